@@ -1,0 +1,200 @@
+/* kanpyo_b200.h — C ABI of the B200-native Kanpyo hot path (lattice build + Viterbi).
+ *
+ * This is the drop-in boundary for the reference's `Tokenizer::tokenize()` path
+ * (togatoga/kanpyo @ f1931e2c).  Everything behind it is hand-written CUDA for sm_100a; there is
+ * NO CPU fallback: every compute entry point returns KP_ERR_CUDA when no usable GPU is present.
+ *
+ * Plain C: pointers and sizes only, no C++/torch types.  All functions return 0 (KP_OK) or a
+ * negative kp_status; nothing throws across the boundary.  A Rust/ctypes/cgo caller binds exactly
+ * these symbols (see INTEGRATION.md for the Rust shim that keeps the reference's signatures).
+ *
+ * Reference interfaces replaced (file:line relative to the reference tree):
+ *   kp_dict_create            <- the fields of `Dict` the hot path reads           kanpyo-dict/src/dict.rs:21-30
+ *                                (IndexTable{da,dup} index.rs:10-13, Morphs morph.rs:24,
+ *                                 ConnectionTable connection.rs:5-9, CharCategoryDef
+ *                                 char_category_def.rs:15-20, UnkDict unk_dict.rs:12-16)
+ *   kp_tokenizer_create       <- Tokenizer::new(dict)                               src/tokenizer.rs:12-14
+ *   kp_tokenize               <- Tokenizer::tokenize(&self, &str) -> Vec<Token>     src/tokenizer.rs:16-45
+ *   kp_tokenize_batch[_device]<- the same call over many independent sentences (new: the reference
+ *                                has no batch entry; semantics = tokenize() per sentence)
+ *   kp_token                  <- Token / TokenClass                                 src/token.rs:4-18
+ *   kp_lattice_dump           <- Lattice::build + Lattice::viterbi (pub nodes/edges) src/lattice.rs:6-10,101,116
+ *   kp_da_common_prefix       <- IndexTable::search_common_prefix_of                kanpyo-dict/src/index.rs:40-53
+ *                                (DoubleArray::search_common_prefix_of              kanpyo-dict/src/trie/da.rs:155-182)
+ */
+#ifndef KANPYO_B200_H
+#define KANPYO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KP_ABI_VERSION 1
+
+typedef enum kp_status {
+    KP_OK = 0,
+    KP_ERR_ARG = -1,          /* null pointer / inconsistent sizes / offsets not ascending */
+    KP_ERR_CUDA = -2,         /* CUDA runtime error or no sm_100 device (kp_last_error() has the text) */
+    KP_ERR_DICT = -3,         /* dictionary arrays fail validation (an index the reference would panic on) */
+    KP_ERR_UTF8 = -4,         /* input is not valid UTF-8 (Rust's &str guarantees validity; the ABI checks) */
+    KP_ERR_NOMEM = -5,        /* host or device allocation failed */
+    KP_ERR_TOO_LARGE = -6,    /* a single chunk exceeds the 2^31-byte / 2^32-node device index range */
+    KP_ERR_BLOB = -7          /* packed dictionary blob has a bad magic / version / size */
+} kp_status;
+
+/* TokenClass (src/token.rs:4-8) */
+enum { KP_CLASS_DUMMY = 0, KP_CLASS_KNOWN = 1, KP_CLASS_UNKNOWN = 2 };
+
+/* Host arrays describing the read-only dictionary, exactly the data the reference's hot path reads.
+ * Nothing is retained after kp_dict_create returns. */
+typedef struct kp_dict_arrays {
+    const int32_t* da;              /* [da_len][2] = {base, check}                      da.rs:14-20 */
+    uint64_t da_len;
+    const int64_t* dup_ids;         /* BTreeMap<KeywordID,usize> keys                   index.rs:12 */
+    const uint64_t* dup_counts;     /*                           values                             */
+    uint64_t n_dup;
+    const int16_t* morphs;          /* [n_morphs][3] = {left_id, right_id, cost}        morph.rs:7-11,24 */
+    uint64_t n_morphs;
+    uint64_t conn_row, conn_col;    /* ConnectionTable{row,col}; get(r,c)=data[row*c+r] connection.rs:5-14 */
+    const int16_t* conn;            /* [conn_row*conn_col]                                           */
+    const uint8_t* char_category;   /* [n_char_category] code point -> class            char_category_def.rs:15-38 */
+    uint64_t n_char_category;
+    const uint8_t* invoke_list;     /* [n_invoke] bool                                  char_category_def.rs:18 */
+    uint64_t n_invoke;
+    const uint8_t* group_list;      /* [n_group] bool                                   char_category_def.rs:19 */
+    uint64_t n_group;
+    const uint8_t* unk_cat;         /* BTreeMap<u8,(KeywordID,usize)> keys              unk_dict.rs:15 */
+    const int64_t* unk_first_id;    /*   .0 : first 1-based unknown morph id                          */
+    const uint64_t* unk_count;      /*   .1 : number of consecutive ids                               */
+    uint64_t n_unk_map;
+    const int16_t* unk_morphs;      /* [n_unk_morphs][3]                                unk_dict.rs:13 */
+    uint64_t n_unk_morphs;
+} kp_dict_arrays;
+
+typedef struct kp_dict kp_dict;             /* immutable, device-resident; shareable across tokenizers/threads */
+typedef struct kp_tokenizer kp_tokenizer;   /* one CUDA stream + scratch; NOT thread-safe (one per caller thread) */
+
+/* Token (src/token.rs:11-18) without the heap string.  `end` = start + char_len.  `surface` is "EOS"
+ * for KP_CLASS_DUMMY (src/tokenizer.rs:28-31); otherwise it is the sentence's bytes
+ * [position, next.position) where `next` is the following token of the same sentence: consecutive
+ * path nodes are adjacent in the input (src/lattice.rs:124-125 pairs a node only with nodes ending
+ * where it starts) and every non-empty path ends with the EOS token, whose position = sentence length. */
+typedef struct kp_token {
+    int32_t id;          /* Token.id (KeywordID); 0 for EOS                                      */
+    uint32_t position;   /* Token.position: byte offset inside its sentence                      */
+    uint32_t start;      /* Token.start: char offset inside its sentence                         */
+    uint16_t char_len;   /* Token.end - Token.start (EOS: 3 = "EOS".chars().count())             */
+    uint8_t cls;         /* KP_CLASS_*                                                           */
+    uint8_t reserved;    /* 0                                                                    */
+} kp_token;              /* 16 bytes */
+
+/* Result of a batch call.  Pointers are owned by the tokenizer and stay valid until its next call
+ * or kp_tokenizer_destroy.  For kp_tokenize_batch they are (pinned) HOST pointers; for
+ * kp_tokenize_batch_device they are DEVICE pointers on the tokenizer's device. */
+typedef struct kp_result {
+    uint64_t n_sent;
+    uint64_t n_tokens;
+    const uint64_t* tok_off;    /* [n_sent+1]: tokens of sentence s are tokens[tok_off[s] .. tok_off[s+1]) */
+    const kp_token* tokens;     /* [n_tokens]                                                              */
+    const int32_t* eos_cost;    /* [n_sent]: dp[EOS] of Lattice::viterbi (src/lattice.rs:116-143)          */
+} kp_result;
+
+/* Exact work counters of the last batch call (used for the roofline's algorithmic bytes). */
+typedef struct kp_counters {
+    uint64_t bytes;      /* B: input bytes            */
+    uint64_t chars;      /* C: input chars            */
+    uint64_t nodes;      /* N: lattice nodes incl. BOS and EOS, as in Lattice.nodes.len() summed */
+    uint64_t tokens;     /* T: emitted tokens         */
+    uint64_t sentences;
+    /* filled only when kp_tokenizer_set_count_work(t, 1) was called (extra counting kernels run): */
+    uint64_t probes;     /* P: trie transitions attempted   (da.rs:160-162)                      */
+    uint64_t probes_ok;  /* P_ok: transitions whose check matched (then read `ahead`, da.rs:166-167) */
+    uint64_t pairs;      /* E: (target, previous) pairs visited by viterbi (lattice.rs:125)      */
+} kp_counters;
+
+/* Per-stage device times of the last batch call, CUDA events on the tokenizer's stream (milliseconds). */
+typedef struct kp_profile {
+    float h2d_ms, prep_ms, lattice_ms, bucket_ms, viterbi_ms, backtrace_ms, d2h_ms, total_ms;
+    uint32_t kernel_launches;   /* kernels of this library launched by the call */
+    uint32_t chunks;
+} kp_profile;
+
+int kp_abi_version(void);
+const char* kp_strerror(int status);
+const char* kp_last_error(void);            /* thread-local detail for the last failing call */
+int kp_device_count(int* n);                /* CUDA devices visible to the library            */
+
+/* ---- dictionary ------------------------------------------------------------------------------- */
+/* Validates every index the hot path can form (KP_ERR_DICT instead of the reference's panic), packs
+ * the arrays into one blob and stages it to HBM on `device` once. */
+int kp_dict_create(const kp_dict_arrays* arrays, int device, kp_dict** out);
+/* Validate + pack only (host work, no device needed).  dst == NULL: just report *size. */
+int kp_dict_pack(const kp_dict_arrays* arrays, void* dst, uint64_t cap, uint64_t* size);
+/* The packed blob (host copy kept by the handle / the staged copy in HBM): what a multi-GPU launcher
+ * broadcasts to the other ranks. */
+int kp_dict_blob(const kp_dict* d, const void** host_ptr, uint64_t* size);
+int kp_dict_device_blob(const kp_dict* d, const void** device_ptr, uint64_t* size);
+/* Build a handle from a packed blob in host memory, or from one already in device memory (e.g. the
+ * receive buffer of an NCCL broadcast). */
+int kp_dict_create_from_blob(const void* host_blob, uint64_t size, int device, kp_dict** out);
+int kp_dict_create_from_device_blob(const void* device_blob, uint64_t size, int device, kp_dict** out);
+void kp_dict_destroy(kp_dict* d);
+
+/* ---- tokenizer -------------------------------------------------------------------------------- */
+int kp_tokenizer_create(const kp_dict* d, kp_tokenizer** out);     /* Tokenizer::new */
+void kp_tokenizer_destroy(kp_tokenizer* t);
+/* Upper bound on input bytes processed per device pass by kp_tokenize_batch (default 64 MiB). */
+int kp_tokenizer_set_chunk_bytes(kp_tokenizer* t, uint64_t bytes);
+
+/* Tokenizer::tokenize for one sentence (host UTF-8, not NUL-terminated). */
+int kp_tokenize(kp_tokenizer* t, const uint8_t* utf8, uint64_t len, kp_result* out);
+/* Sentences s = utf8[offsets[s] .. offsets[s+1]) for s in [0,n_sent); HOST pointers in, HOST result out. */
+int kp_tokenize_batch(kp_tokenizer* t, const uint8_t* utf8, const uint64_t* offsets, uint64_t n_sent,
+                      kp_result* out);
+/* Same, with utf8/offsets already resident in device memory and the result left in device memory.
+ * n_bytes = offsets[n_sent] - offsets[0] (the host must know it).  The batch is one device pass. */
+int kp_tokenize_batch_device(kp_tokenizer* t, const uint8_t* d_utf8, const uint64_t* d_offsets, uint64_t n_sent,
+                             uint64_t first_offset, uint64_t n_bytes, kp_result* out);
+int kp_last_counters(const kp_tokenizer* t, kp_counters* out);
+/* on != 0: also count P, P_ok, E (slower; never enabled inside a timed region). */
+int kp_tokenizer_set_count_work(kp_tokenizer* t, int on);
+int kp_last_profile(const kp_tokenizer* t, kp_profile* out);
+/* Copy `bytes` from device memory of a kp_tokenize_batch_device result to host memory (for callers
+ * that do not bind a CUDA runtime themselves). */
+int kp_copy_to_host(kp_tokenizer* t, void* dst, const void* device_src, uint64_t bytes);
+/* Blocks until all work queued by this tokenizer is complete. */
+int kp_tokenizer_sync(kp_tokenizer* t);
+
+/* ---- lattice inspection (Lattice{nodes,edges} + viterbi internals) ---------------------------- */
+typedef struct kp_lattice_node {
+    int32_t id;          /* node.id(): 0 for BOS/EOS                    src/lattice/node.rs:27-33 */
+    uint8_t cls;         /* KP_CLASS_* (Dummy = BOS/EOS)                                          */
+    uint8_t reserved[3];
+    uint32_t byte_pos;   /* node.byte_pos()                                                       */
+    uint32_t char_pos;   /* node.char_pos()                                                       */
+    uint32_t end_char;   /* index of the `edges` bucket holding the node (BOS 0, EOS n+1)         */
+    int16_t left_id, right_id, cost;
+    int16_t reserved2;
+    int32_t dp;          /* dp[i] after viterbi(); INT32_MIN where the reference has None (BOS)   */
+    int32_t pre;         /* pre_nodes[i] as a node index; -1 where the reference has None         */
+} kp_lattice_node;       /* 36 bytes */
+
+typedef struct kp_lattice {
+    uint64_t n_nodes;                /* nodes in the reference's insertion order (BOS first, EOS last) */
+    const kp_lattice_node* nodes;    /* HOST pointer, owned by the tokenizer                           */
+} kp_lattice;
+int kp_lattice_dump(kp_tokenizer* t, const uint8_t* utf8, uint64_t len, kp_lattice* out);
+
+/* IndexTable::search_common_prefix_of on the device copy of the trie (one query; for parity tests
+ * of the reference's known-answer vectors).  Writes up to `cap` (id, byte_len) pairs; *n = total hits
+ * (0 where the reference returns None). */
+int kp_da_common_prefix(kp_tokenizer* t, const uint8_t* utf8, uint64_t len, int expand_dup, int64_t* ids,
+                        uint64_t* byte_lens, uint64_t cap, uint64_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KANPYO_B200_H */

@@ -1,0 +1,58 @@
+"""Builds libkanpyo_b200.so (the C-ABI library of include/kanpyo_b200.h) in-tree with nvcc for sm_100a.
+
+    python -m kanpyo_b200.build [--force]
+
+The library links the CUDA runtime statically, so it has no dependency on PyTorch or on the
+libcudart that PyTorch ships.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libkanpyo_b200.so")
+SOURCES = ["kp_dict.cu", "kp_kernels.cu", "kp_api.cu", "kp_dictbuild.cpp"]
+HEADERS = ["kp_common.cuh", "kp_kernels.cuh", os.path.join("..", "..", "include", "kanpyo_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-Xptxas", "-v", "-shared", "-cudart", "static"]
+
+
+def nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; kanpyo_b200 cannot be built (there is no CPU fallback)")
+
+
+def stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not stale():
+        return LIB
+    srcs = [os.path.join(CSRC, f) for f in SOURCES if os.path.exists(os.path.join(CSRC, f))]
+    cmd = [nvcc()] + NVCC_FLAGS + ["-o", LIB + ".tmp"] + srcs
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building libkanpyo_b200.so")
+    os.replace(LIB + ".tmp", LIB)
+    log = os.path.join(HERE, "_build_ptxas.log")
+    with open(log, "w") as f:
+        f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if verbose:
+        sys.stderr.write(r.stdout + r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,511 @@
+// kp_api.cu — tokenizer handle, chunk pipeline and the C ABI entry points of include/kanpyo_b200.h.
+//
+// Host-side mirror of the reference's `Tokenizer` (src/tokenizer.rs:7-45): `kp_tokenizer_create` is
+// Tokenizer::new, `kp_tokenize` is Tokenizer::tokenize; the batch calls run the same function over
+// many independent sentences in one device pass.  There is no CPU implementation behind any of them.
+#include <limits.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "kp_kernels.cuh"
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return KP_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            kp_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+            p = nullptr;
+            return KP_ERR_NOMEM;
+        }
+        cap = want;
+        return KP_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return (T*)p; }
+};
+
+struct PinBuf {   // pinned host memory, preserved on growth
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes, size_t keep) {
+        if (bytes <= cap) return KP_OK;
+        size_t want = std::max(bytes, cap * 2) + 4096;
+        void* q = nullptr;
+        cudaError_t e = cudaHostAlloc(&q, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            kp_set_error("cudaHostAlloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            return KP_ERR_NOMEM;
+        }
+        if (p && keep) memcpy(q, p, keep);
+        if (p) cudaFreeHost(p);
+        p = q;
+        cap = want;
+        return KP_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return (T*)p; }
+};
+
+enum { EV_START, EV_H2D, EV_PREP, EV_LATTICE, EV_BUCKET, EV_VITERBI, EV_BACKTRACE, EV_END, EV_COUNT };
+
+}  // namespace
+
+struct kp_tokenizer {
+    const kp_dict* dict = nullptr;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[EV_COUNT] = {};
+    uint64_t chunk_bytes = 64ull << 20;
+    bool count_work = false;
+    // chunk scratch
+    DevBuf text, off, nchar, coff, binfo, ncount, noff, bcount, boff, bfill, rec, slot, bright, bnode, bdp, pre,
+        tcount, toff32, scan_tmp, totals, err;
+    // device outputs
+    DevBuf d_tok_off, d_tokens, d_eos;
+    // host staging
+    PinBuf h_totals, h_tok_off, h_tokens, h_eos, h_misc;
+    std::vector<kp_lattice_node> lattice_nodes;
+    kp_counters counters = {};
+    kp_profile profile = {};
+};
+
+namespace {
+
+#define KP_TRY(x)            \
+    do {                     \
+        int rc__ = (x);      \
+        if (rc__ < 0) return rc__; \
+    } while (0)
+#define KP_LAUNCH(x)                         \
+    do {                                     \
+        int rc__ = (x);                      \
+        if (rc__ < 0) return rc__;           \
+        t->profile.kernel_launches += rc__;  \
+    } while (0)
+
+struct StageTimes {
+    float prep = 0, lattice = 0, bucket = 0, viterbi = 0, backtrace = 0;
+};
+
+// One device pass over a chunk whose text / offsets are already in device memory.
+// Results land in t->d_tok_off[tok_off_pos ..], t->d_tokens[tok_base ..], t->d_eos[sent_pos ..]
+// when `append` (device API) or at position 0 (host API copies them out per chunk).
+int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_tokens, StageTimes* times) {
+    cudaStream_t st = t->stream;
+    const kp_ddict& d = t->dict->view;
+    const uint32_t S = c.S;
+    KP_TRY(t->nchar.ensure(sizeof(uint32_t) * (S + 1)));
+    KP_TRY(t->coff.ensure(sizeof(uint32_t) * (S + 2)));
+    KP_TRY(t->totals.ensure(sizeof(uint64_t) * 8));
+    KP_TRY(t->err.ensure(sizeof(uint32_t) * 2));
+    KP_TRY(t->h_totals.ensure(sizeof(uint64_t) * 16, 0));
+    KP_TRY(t->scan_tmp.ensure(sizeof(uint64_t) * kp_scan_tmp_elems(S + 1)));
+    c.nchar = t->nchar.as<uint32_t>();
+    c.coff = t->coff.as<uint32_t>();
+    c.totals = t->totals.as<uint64_t>();
+    c.err = t->err.as<uint32_t>();
+    c.scan_tmp = t->scan_tmp.as<uint64_t>();
+    uint64_t* h_tot = t->h_totals.as<uint64_t>();
+    uint32_t* h_err = (uint32_t*)(h_tot + 8);
+
+    KP_CUDA(cudaEventRecord(t->ev[EV_H2D], st));
+    KP_CUDA(cudaMemsetAsync(c.totals, 0, sizeof(uint64_t) * 8, st));
+    KP_CUDA(cudaMemsetAsync(c.err, 0, sizeof(uint32_t) * 2, st));
+    KP_LAUNCH(kp_launch_prep_count(c, st));
+    KP_LAUNCH(kp_launch_scan(c.nchar, c.coff, S, c.scan_tmp, &c.totals[0], st));
+    KP_CUDA(cudaMemcpyAsync(h_tot, c.totals, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaMemcpyAsync(h_err, c.err, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaStreamSynchronize(st));
+    if (h_err[1]) {
+        kp_set_error("sentence offsets are not ascending or exceed the text length");
+        return KP_ERR_ARG;
+    }
+    if (h_err[0]) {
+        kp_set_error("input contains invalid UTF-8");
+        return KP_ERR_UTF8;
+    }
+    if (h_tot[0] + S + 1 >= (1ull << 32)) return KP_ERR_TOO_LARGE;
+    c.C = (uint32_t)h_tot[0];
+    c.NB = c.C + S;
+    const size_t NB = c.NB;
+    KP_TRY(t->binfo.ensure(sizeof(uint4) * (NB + 1)));
+    KP_TRY(t->ncount.ensure(sizeof(uint32_t) * (NB + 1)));
+    KP_TRY(t->noff.ensure(sizeof(uint32_t) * (NB + 2)));
+    KP_TRY(t->bcount.ensure(sizeof(uint32_t) * (NB + 1)));
+    KP_TRY(t->boff.ensure(sizeof(uint32_t) * (NB + 2)));
+    KP_TRY(t->bfill.ensure(sizeof(uint32_t) * (NB + 1)));
+    KP_TRY(t->scan_tmp.ensure(sizeof(uint64_t) * kp_scan_tmp_elems((uint32_t)NB + 1)));
+    c.scan_tmp = t->scan_tmp.as<uint64_t>();
+    c.binfo = t->binfo.as<uint4>();
+    c.ncount = t->ncount.as<uint32_t>();
+    c.noff = t->noff.as<uint32_t>();
+    c.bcount = t->bcount.as<uint32_t>();
+    c.boff = t->boff.as<uint32_t>();
+    c.bfill = t->bfill.as<uint32_t>();
+
+    KP_LAUNCH(kp_launch_prep_fill(c, d, st));
+    KP_CUDA(cudaEventRecord(t->ev[EV_PREP], st));
+    KP_LAUNCH(kp_launch_lattice_count(c, d, t->count_work, st));
+    KP_LAUNCH(kp_launch_scan2(c.ncount, c.bcount, c.noff, c.boff, c.NB, c.scan_tmp, &c.totals[1], &c.totals[2], st));
+    KP_CUDA(cudaMemcpyAsync(h_tot, c.totals, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaStreamSynchronize(st));
+    if (h_tot[1] >= (1ull << 32) - 1) return KP_ERR_TOO_LARGE;
+    c.N = (uint32_t)h_tot[1];
+    if (h_tot[2] != h_tot[1]) {
+        kp_set_error("internal: bucket entries %llu != nodes %llu", (unsigned long long)h_tot[2],
+                     (unsigned long long)h_tot[1]);
+        return KP_ERR_CUDA;
+    }
+    const size_t N = c.N;
+    KP_TRY(t->rec.ensure(sizeof(uint4) * (N + 1)));
+    KP_TRY(t->slot.ensure(sizeof(uint32_t) * (N + 1)));
+    KP_TRY(t->bright.ensure(sizeof(int16_t) * (N + 2)));
+    KP_TRY(t->bnode.ensure(sizeof(uint32_t) * (N + 1)));
+    KP_TRY(t->bdp.ensure(sizeof(int32_t) * (N + 1)));
+    KP_TRY(t->pre.ensure(sizeof(uint32_t) * (N + 1)));
+    KP_TRY(t->tcount.ensure(sizeof(uint32_t) * (S + 1)));
+    KP_TRY(t->toff32.ensure(sizeof(uint32_t) * (S + 2)));
+    c.rec = t->rec.as<uint4>();
+    c.slot = t->slot.as<uint32_t>();
+    c.bright = t->bright.as<int16_t>();
+    c.bnode = t->bnode.as<uint32_t>();
+    c.bdp = t->bdp.as<int32_t>();
+    c.pre = t->pre.as<uint32_t>();
+    c.tcount = t->tcount.as<uint32_t>();
+    c.toff32 = t->toff32.as<uint32_t>();
+
+    KP_LAUNCH(kp_launch_lattice_fill(c, d, st));
+    KP_CUDA(cudaEventRecord(t->ev[EV_LATTICE], st));
+    KP_CUDA(cudaMemsetAsync(c.bfill, 0, sizeof(uint32_t) * (NB + 1), st));
+    KP_LAUNCH(kp_launch_bucketize(c, st));
+    KP_CUDA(cudaEventRecord(t->ev[EV_BUCKET], st));
+    KP_LAUNCH(kp_launch_viterbi(c, d, st));
+    if (t->count_work) KP_LAUNCH(kp_launch_pair_count(c, st));
+    KP_CUDA(cudaEventRecord(t->ev[EV_VITERBI], st));
+    KP_LAUNCH(kp_launch_backtrace_count(c, st));
+    KP_LAUNCH(kp_launch_scan(c.tcount, c.toff32, S, c.scan_tmp, &c.totals[3], st));
+    KP_LAUNCH(kp_launch_backtrace_write(c, tok_base, st));
+    KP_CUDA(cudaEventRecord(t->ev[EV_BACKTRACE], st));
+    KP_CUDA(cudaMemcpyAsync(h_tot, c.totals, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaStreamSynchronize(st));
+    *n_tokens = h_tot[3];
+    t->counters.bytes += c.B;
+    t->counters.chars += c.C;
+    t->counters.nodes += (uint64_t)c.N + S;   // + one BOS per sentence (not materialised on the device)
+    t->counters.tokens += h_tot[3];
+    t->counters.sentences += S;
+    t->counters.probes += h_tot[4];
+    t->counters.probes_ok += h_tot[5];
+    t->counters.pairs += h_tot[6];
+    if (times) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t->ev[EV_H2D], t->ev[EV_PREP]);       times->prep += ms;
+        cudaEventElapsedTime(&ms, t->ev[EV_PREP], t->ev[EV_LATTICE]);   times->lattice += ms;
+        cudaEventElapsedTime(&ms, t->ev[EV_LATTICE], t->ev[EV_BUCKET]); times->bucket += ms;
+        cudaEventElapsedTime(&ms, t->ev[EV_BUCKET], t->ev[EV_VITERBI]); times->viterbi += ms;
+        cudaEventElapsedTime(&ms, t->ev[EV_VITERBI], t->ev[EV_BACKTRACE]); times->backtrace += ms;
+    }
+    t->profile.chunks++;
+    return KP_OK;
+}
+
+void begin_call(kp_tokenizer* t) {
+    memset(&t->counters, 0, sizeof(t->counters));
+    memset(&t->profile, 0, sizeof(t->profile));
+}
+
+void store_times(kp_tokenizer* t, const StageTimes& s) {
+    t->profile.prep_ms = s.prep;
+    t->profile.lattice_ms = s.lattice;
+    t->profile.bucket_ms = s.bucket;
+    t->profile.viterbi_ms = s.viterbi;
+    t->profile.backtrace_ms = s.backtrace;
+}
+
+}  // namespace
+
+extern "C" int kp_tokenizer_create(const kp_dict* d, kp_tokenizer** out) {
+    if (!d || !out) return KP_ERR_ARG;
+    *out = nullptr;
+    KP_CUDA(cudaSetDevice(d->device));
+    kp_tokenizer* t = new kp_tokenizer();
+    t->dict = d;
+    t->device = d->device;
+    cudaError_t e = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < EV_COUNT && e == cudaSuccess; i++) e = cudaEventCreate(&t->ev[i]);
+    if (e != cudaSuccess) {
+        kp_set_error("stream/event creation failed: %s", cudaGetErrorString(e));
+        delete t;
+        return KP_ERR_CUDA;
+    }
+    *out = t;
+    return KP_OK;
+}
+
+extern "C" void kp_tokenizer_destroy(kp_tokenizer* t) {
+    if (!t) return;
+    cudaSetDevice(t->device);
+    if (t->stream) cudaStreamSynchronize(t->stream);
+    DevBuf* bufs[] = {&t->text, &t->off, &t->nchar, &t->coff, &t->binfo, &t->ncount, &t->noff, &t->bcount, &t->boff,
+                      &t->bfill, &t->rec, &t->slot, &t->bright, &t->bnode, &t->bdp, &t->pre, &t->tcount, &t->toff32,
+                      &t->scan_tmp, &t->totals, &t->err, &t->d_tok_off, &t->d_tokens, &t->d_eos};
+    for (DevBuf* b : bufs) b->release();
+    PinBuf* pins[] = {&t->h_totals, &t->h_tok_off, &t->h_tokens, &t->h_eos, &t->h_misc};
+    for (PinBuf* b : pins) b->release();
+    for (int i = 0; i < EV_COUNT; i++)
+        if (t->ev[i]) cudaEventDestroy(t->ev[i]);
+    if (t->stream) cudaStreamDestroy(t->stream);
+    delete t;
+}
+
+extern "C" int kp_tokenizer_set_chunk_bytes(kp_tokenizer* t, uint64_t bytes) {
+    if (!t || bytes == 0) return KP_ERR_ARG;
+    t->chunk_bytes = std::min<uint64_t>(bytes, (1ull << 31) - 1);
+    return KP_OK;
+}
+
+extern "C" int kp_tokenizer_set_count_work(kp_tokenizer* t, int on) {
+    if (!t) return KP_ERR_ARG;
+    t->count_work = on != 0;
+    return KP_OK;
+}
+
+extern "C" int kp_tokenizer_sync(kp_tokenizer* t) {
+    if (!t) return KP_ERR_ARG;
+    KP_CUDA(cudaSetDevice(t->device));
+    KP_CUDA(cudaStreamSynchronize(t->stream));
+    return KP_OK;
+}
+
+extern "C" int kp_copy_to_host(kp_tokenizer* t, void* dst, const void* device_src, uint64_t bytes) {
+    if (!t || (bytes && (!dst || !device_src))) return KP_ERR_ARG;
+    KP_CUDA(cudaSetDevice(t->device));
+    if (bytes) {
+        KP_CUDA(cudaMemcpyAsync(dst, device_src, bytes, cudaMemcpyDeviceToHost, t->stream));
+        KP_CUDA(cudaStreamSynchronize(t->stream));
+    }
+    return KP_OK;
+}
+
+extern "C" int kp_last_counters(const kp_tokenizer* t, kp_counters* out) {
+    if (!t || !out) return KP_ERR_ARG;
+    *out = t->counters;
+    return KP_OK;
+}
+
+extern "C" int kp_last_profile(const kp_tokenizer* t, kp_profile* out) {
+    if (!t || !out) return KP_ERR_ARG;
+    *out = t->profile;
+    return KP_OK;
+}
+
+extern "C" int kp_tokenize_batch_device(kp_tokenizer* t, const uint8_t* d_utf8, const uint64_t* d_offsets,
+                                        uint64_t n_sent, uint64_t first_offset, uint64_t n_bytes, kp_result* out) {
+    if (!t || !out || !d_offsets || (n_bytes && !d_utf8)) return KP_ERR_ARG;
+    if (n_bytes >= (1ull << 31) || n_sent >= (1ull << 31) - 2) return KP_ERR_TOO_LARGE;
+    KP_CUDA(cudaSetDevice(t->device));
+    begin_call(t);
+    cudaStream_t st = t->stream;
+    kp_chunk c;
+    memset(&c, 0, sizeof(c));
+    c.text = d_utf8 + first_offset;
+    c.off = d_offsets;
+    c.base = first_offset;
+    c.S = (uint32_t)n_sent;
+    c.B = (uint32_t)n_bytes;
+    // tokens <= chars + sentences <= bytes + sentences: size the outputs without a device round trip
+    KP_TRY(t->d_tok_off.ensure(sizeof(uint64_t) * (n_sent + 1)));
+    KP_TRY(t->d_eos.ensure(sizeof(int32_t) * (n_sent + 1)));
+    KP_TRY(t->d_tokens.ensure(sizeof(kp_token) * (n_bytes + n_sent + 1)));
+    c.tok_off = t->d_tok_off.as<uint64_t>();
+    c.eos_cost = t->d_eos.as<int32_t>();
+    c.tokens = t->d_tokens.as<kp_token>();
+    KP_CUDA(cudaEventRecord(t->ev[EV_START], st));
+    uint64_t ntok = 0;
+    StageTimes times;
+    KP_TRY(run_chunk(t, c, 0, &ntok, &times));
+    KP_CUDA(cudaEventRecord(t->ev[EV_END], st));
+    KP_CUDA(cudaEventSynchronize(t->ev[EV_END]));
+    store_times(t, times);
+    cudaEventElapsedTime(&t->profile.total_ms, t->ev[EV_START], t->ev[EV_END]);
+    out->n_sent = n_sent;
+    out->n_tokens = ntok;
+    out->tok_off = c.tok_off;
+    out->tokens = c.tokens;
+    out->eos_cost = c.eos_cost;
+    return KP_OK;
+}
+
+extern "C" int kp_tokenize_batch(kp_tokenizer* t, const uint8_t* utf8, const uint64_t* offsets, uint64_t n_sent,
+                                 kp_result* out) {
+    if (!t || !out || !offsets) return KP_ERR_ARG;
+    if (n_sent && offsets[n_sent] > offsets[0] && !utf8) return KP_ERR_ARG;
+    for (uint64_t s = 0; s < n_sent; s++)
+        if (offsets[s + 1] < offsets[s]) {
+            kp_set_error("offsets[%llu] > offsets[%llu]", (unsigned long long)s, (unsigned long long)(s + 1));
+            return KP_ERR_ARG;
+        }
+    KP_CUDA(cudaSetDevice(t->device));
+    begin_call(t);
+    cudaStream_t st = t->stream;
+    KP_TRY(t->h_tok_off.ensure(sizeof(uint64_t) * (n_sent + 1), 0));
+    KP_TRY(t->h_eos.ensure(sizeof(int32_t) * (n_sent + 1), 0));
+    t->h_tok_off.as<uint64_t>()[0] = 0;
+    uint64_t tok_total = 0;
+    StageTimes times;
+    float h2d_ms = 0, d2h_ms = 0, total_ms = 0;
+    uint64_t s0 = 0;
+    while (s0 < n_sent) {
+        // greedy chunk: as many whole sentences as fit in chunk_bytes (at least one)
+        uint64_t s1 = s0 + 1;
+        while (s1 < n_sent && offsets[s1 + 1] - offsets[s0] <= t->chunk_bytes && s1 - s0 < (1u << 30)) s1++;
+        const uint64_t nbytes = offsets[s1] - offsets[s0];
+        const uint64_t S = s1 - s0;
+        if (nbytes >= (1ull << 31)) return KP_ERR_TOO_LARGE;
+        KP_TRY(t->text.ensure(nbytes + 16));
+        KP_TRY(t->off.ensure(sizeof(uint64_t) * (S + 1)));
+        KP_TRY(t->d_tok_off.ensure(sizeof(uint64_t) * (S + 1)));
+        KP_TRY(t->d_eos.ensure(sizeof(int32_t) * (S + 1)));
+        KP_TRY(t->d_tokens.ensure(sizeof(kp_token) * (nbytes + S + 1)));
+        KP_CUDA(cudaEventRecord(t->ev[EV_START], st));
+        if (nbytes) KP_CUDA(cudaMemcpyAsync(t->text.p, utf8 + offsets[s0], nbytes, cudaMemcpyHostToDevice, st));
+        KP_CUDA(cudaMemcpyAsync(t->off.p, offsets + s0, sizeof(uint64_t) * (S + 1), cudaMemcpyHostToDevice, st));
+        kp_chunk c;
+        memset(&c, 0, sizeof(c));
+        c.text = t->text.as<uint8_t>();
+        c.off = t->off.as<uint64_t>();
+        c.base = offsets[s0];
+        c.S = (uint32_t)S;
+        c.B = (uint32_t)nbytes;
+        c.tok_off = t->d_tok_off.as<uint64_t>();
+        c.eos_cost = t->d_eos.as<int32_t>();
+        c.tokens = t->d_tokens.as<kp_token>();
+        uint64_t ntok = 0;
+        KP_TRY(run_chunk(t, c, tok_total, &ntok, &times));
+        KP_TRY(t->h_tokens.ensure(sizeof(kp_token) * (tok_total + ntok + 1), sizeof(kp_token) * tok_total));
+        if (ntok)
+            KP_CUDA(cudaMemcpyAsync(t->h_tokens.as<kp_token>() + tok_total, c.tokens, sizeof(kp_token) * ntok,
+                                    cudaMemcpyDeviceToHost, st));
+        KP_CUDA(cudaMemcpyAsync(t->h_tok_off.as<uint64_t>() + s0, c.tok_off, sizeof(uint64_t) * (S + 1),
+                                cudaMemcpyDeviceToHost, st));
+        KP_CUDA(cudaMemcpyAsync(t->h_eos.as<int32_t>() + s0, c.eos_cost, sizeof(int32_t) * S, cudaMemcpyDeviceToHost, st));
+        KP_CUDA(cudaEventRecord(t->ev[EV_END], st));
+        KP_CUDA(cudaEventSynchronize(t->ev[EV_END]));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t->ev[EV_START], t->ev[EV_H2D]);    h2d_ms += ms;
+        cudaEventElapsedTime(&ms, t->ev[EV_BACKTRACE], t->ev[EV_END]); d2h_ms += ms;
+        cudaEventElapsedTime(&ms, t->ev[EV_START], t->ev[EV_END]);     total_ms += ms;
+        tok_total += ntok;
+        s0 = s1;
+    }
+    store_times(t, times);
+    t->profile.h2d_ms = h2d_ms;
+    t->profile.d2h_ms = d2h_ms;
+    t->profile.total_ms = total_ms;
+    out->n_sent = n_sent;
+    out->n_tokens = tok_total;
+    out->tok_off = t->h_tok_off.as<uint64_t>();
+    out->tokens = t->h_tokens.as<kp_token>();
+    out->eos_cost = t->h_eos.as<int32_t>();
+    return KP_OK;
+}
+
+extern "C" int kp_tokenize(kp_tokenizer* t, const uint8_t* utf8, uint64_t len, kp_result* out) {
+    const uint64_t off[2] = {0, len};
+    return kp_tokenize_batch(t, utf8, off, 1, out);
+}
+
+// Lattice::build + viterbi internals of one sentence, in the reference's node order (BOS first).
+extern "C" int kp_lattice_dump(kp_tokenizer* t, const uint8_t* utf8, uint64_t len, kp_lattice* out) {
+    if (!t || !out || (len && !utf8)) return KP_ERR_ARG;
+    kp_result r;
+    KP_TRY(kp_tokenize(t, utf8, len, &r));
+    // scratch of the (single-chunk) pass is still intact
+    const uint32_t N = (uint32_t)(t->counters.nodes - 1);   // device nodes (no BOS)
+    const uint32_t NB = (uint32_t)t->counters.chars + 1;
+    std::vector<uint4> rec(N), binfo(NB);
+    std::vector<uint32_t> slot(N), bnode(N), pre(N);
+    std::vector<int32_t> bdp(N);
+    KP_CUDA(cudaMemcpy(rec.data(), t->rec.p, sizeof(uint4) * N, cudaMemcpyDeviceToHost));
+    KP_CUDA(cudaMemcpy(binfo.data(), t->binfo.p, sizeof(uint4) * NB, cudaMemcpyDeviceToHost));
+    KP_CUDA(cudaMemcpy(slot.data(), t->slot.p, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost));
+    KP_CUDA(cudaMemcpy(bnode.data(), t->bnode.p, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost));
+    KP_CUDA(cudaMemcpy(pre.data(), t->pre.p, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost));
+    KP_CUDA(cudaMemcpy(bdp.data(), t->bdp.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost));
+    t->lattice_nodes.assign((size_t)N + 1, kp_lattice_node{});
+    kp_lattice_node& bos = t->lattice_nodes[0];
+    bos.id = 0;
+    bos.cls = KP_CLASS_DUMMY;
+    bos.dp = INT_MIN;
+    bos.pre = -1;
+    for (uint32_t i = 0; i < N; i++) {
+        kp_lattice_node& o = t->lattice_nodes[i + 1];
+        const uint4 x = rec[i];
+        const uint32_t kind = x.x >> KP_KIND_SHIFT;
+        o.id = (int32_t)(x.x & KP_ID_MASK);
+        o.cls = (uint8_t)kind;
+        o.byte_pos = binfo[x.y].x;
+        o.char_pos = x.y;
+        o.end_char = kind == KP_CLASS_DUMMY ? x.y + 1 : x.y + (x.w >> 16);
+        o.left_id = (int16_t)(x.z & 0xFFFF);
+        o.right_id = (int16_t)(x.z >> 16);
+        o.cost = (int16_t)(x.w & 0xFFFF);
+        o.dp = kind == KP_CLASS_DUMMY ? r.eos_cost[0] : bdp[slot[i]];
+        o.pre = pre[i] == KP_NONE ? -1 : (bnode[pre[i]] == KP_NONE ? 0 : (int32_t)bnode[pre[i]] + 1);
+    }
+    out->n_nodes = (uint64_t)N + 1;
+    out->nodes = t->lattice_nodes.data();
+    return KP_OK;
+}
+
+extern "C" int kp_da_common_prefix(kp_tokenizer* t, const uint8_t* utf8, uint64_t len, int expand_dup, int64_t* ids,
+                                   uint64_t* byte_lens, uint64_t cap, uint64_t* n) {
+    if (!t || !n || (len && !utf8) || (cap && (!ids || !byte_lens)) || len >= (1ull << 31)) return KP_ERR_ARG;
+    KP_CUDA(cudaSetDevice(t->device));
+    cudaStream_t st = t->stream;
+    const uint32_t dcap = (uint32_t)std::min<uint64_t>(cap, 1u << 20);
+    KP_TRY(t->text.ensure(len + 16));
+    KP_TRY(t->rec.ensure(sizeof(int64_t) * (dcap + 1)));
+    KP_TRY(t->bdp.ensure(sizeof(uint64_t) * (dcap + 1)));
+    KP_TRY(t->err.ensure(sizeof(uint32_t) * 2));
+    if (len) KP_CUDA(cudaMemcpyAsync(t->text.p, utf8, len, cudaMemcpyHostToDevice, st));
+    KP_TRY(kp_launch_common_prefix(t->dict->view, t->text.as<uint8_t>(), (uint32_t)len, expand_dup, t->rec.as<int64_t>(),
+                                   t->bdp.as<uint64_t>(), dcap, t->err.as<uint32_t>(), st));
+    uint32_t hn = 0;
+    KP_CUDA(cudaMemcpyAsync(&hn, t->err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaStreamSynchronize(st));
+    const uint32_t m = std::min(hn, dcap);
+    if (m) {
+        KP_CUDA(cudaMemcpy(ids, t->rec.p, sizeof(int64_t) * m, cudaMemcpyDeviceToHost));
+        KP_CUDA(cudaMemcpy(byte_lens, t->bdp.p, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost));
+    }
+    *n = hn;
+    return KP_OK;
+}

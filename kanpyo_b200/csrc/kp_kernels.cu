@@ -1,0 +1,696 @@
+// kp_kernels.cu — hand-written sm_100a kernels of the Kanpyo hot path.
+//
+// Integer / byte work, HBM- and L2-gather bound: no tensor cores.  The dictionary
+// (17.5 MB for IPADIC) is L2-resident on B200 (126 MB L2); node / bucket arrays stream through HBM.
+//
+// Reference semantics implemented (file:line in the reference tree):
+//   trie walk                 DoubleArray::search_common_prefix_of   kanpyo-dict/src/trie/da.rs:155-182
+//   duplicate expansion       IndexTable::search_common_prefix_of    kanpyo-dict/src/index.rs:40-53
+//   known / unknown nodes     Lattice::process_{known,unknown}_words src/lattice.rs:24-99
+//   node order, end buckets   Lattice::add_*_node / `edges`          src/lattice.rs:156-201
+//   forward DP + back-trace   Lattice::viterbi                       src/lattice.rs:116-154
+//   Node -> Token             Tokenizer::tokenize                    src/tokenizer.rs:16-45
+#include "kp_kernels.cuh"
+
+#define KP_FULL 0xFFFFFFFFu
+
+static inline int kp_launch_check(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        kp_set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+        return KP_ERR_CUDA;
+    }
+    return 1;
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// =================================================================================================
+// Exclusive scans (3 launches: tile sums, scan of tile sums, apply).  Two arrays ride together.
+// =================================================================================================
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+uint32_t kp_scan_tmp_elems(uint32_t n) { return 2 * ((n + SCAN_TILE - 1) / SCAN_TILE + 1); }
+
+__device__ __forceinline__ uint64_t block_reduce_u64(uint64_t v, uint64_t* sh) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(KP_FULL, v, o);
+    if (lane_id() == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint64_t r = 0;
+    if (threadIdx.x < 32) {
+        r = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0;
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(KP_FULL, r, o);
+    }
+    return r;  // valid in thread 0
+}
+
+template <bool TWO>
+__global__ void __launch_bounds__(SCAN_THREADS) kp_scan_tile_sums(const uint32_t* __restrict__ a,
+                                                                  const uint32_t* __restrict__ b, uint32_t n,
+                                                                  uint64_t* __restrict__ tmp, uint32_t ntiles) {
+    __shared__ uint64_t sh[SCAN_THREADS / 32];
+    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint64_t sa = 0, sb = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        uint32_t i = base + k;
+        if (i < n) {
+            sa += a[i];
+            if (TWO) sb += b[i];
+        }
+    }
+    uint64_t ra = block_reduce_u64(sa, sh);
+    if (threadIdx.x == 0) tmp[blockIdx.x] = ra;
+    if (TWO) {
+        __syncthreads();
+        uint64_t rb = block_reduce_u64(sb, sh);
+        if (threadIdx.x == 0) tmp[ntiles + blockIdx.x] = rb;
+    }
+}
+
+// one block: exclusive scan of the tile sums in place, totals out
+template <bool TWO>
+__global__ void __launch_bounds__(1024) kp_scan_partials(uint64_t* __restrict__ tmp, uint32_t ntiles,
+                                                         uint32_t* __restrict__ out_a, uint32_t* __restrict__ out_b,
+                                                         uint32_t n, uint64_t* __restrict__ total_a,
+                                                         uint64_t* __restrict__ total_b) {
+    __shared__ uint64_t wsum[32];
+    __shared__ uint64_t carry_sh;
+    for (int arr = 0; arr < (TWO ? 2 : 1); arr++) {
+        uint64_t* t = tmp + (size_t)arr * ntiles;
+        if (threadIdx.x == 0) carry_sh = 0;
+        __syncthreads();
+        for (uint32_t i0 = 0; i0 < ntiles; i0 += 1024) {
+            uint32_t i = i0 + threadIdx.x;
+            uint64_t v = i < ntiles ? t[i] : 0;
+            uint64_t x = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint64_t y = __shfl_up_sync(KP_FULL, x, o);
+                if (lane_id() >= (uint32_t)o) x += y;
+            }
+            if (lane_id() == 31) wsum[threadIdx.x >> 5] = x;
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                uint64_t w = wsum[threadIdx.x];
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint64_t y = __shfl_up_sync(KP_FULL, w, o);
+                    if (lane_id() >= (uint32_t)o) w += y;
+                }
+                wsum[threadIdx.x] = w;  // inclusive over warps
+            }
+            __syncthreads();
+            uint64_t warp_off = (threadIdx.x >> 5) ? wsum[(threadIdx.x >> 5) - 1] : 0;
+            uint64_t carry = carry_sh;
+            if (i < ntiles) t[i] = carry + warp_off + x - v;
+            __syncthreads();
+            if (threadIdx.x == 1023) carry_sh = carry + warp_off + x;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            uint64_t tot = carry_sh;
+            if (arr == 0) {
+                out_a[n] = (uint32_t)tot;
+                if (total_a) *total_a = tot;
+            } else {
+                out_b[n] = (uint32_t)tot;
+                if (total_b) *total_b = tot;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <bool TWO>
+__global__ void __launch_bounds__(SCAN_THREADS) kp_scan_apply(const uint32_t* __restrict__ a,
+                                                              const uint32_t* __restrict__ b, uint32_t n,
+                                                              const uint64_t* __restrict__ tmp, uint32_t ntiles,
+                                                              uint32_t* __restrict__ out_a, uint32_t* __restrict__ out_b) {
+    __shared__ uint32_t wsa[SCAN_THREADS / 32], wsb[SCAN_THREADS / 32];
+    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t va[SCAN_ITEMS], vb[SCAN_ITEMS];
+    uint32_t sa = 0, sb = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        uint32_t i = base + k;
+        va[k] = i < n ? a[i] : 0;
+        sa += va[k];
+        if (TWO) {
+            vb[k] = i < n ? b[i] : 0;
+            sb += vb[k];
+        }
+    }
+    uint32_t xa = sa, xb = sb;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t ya = __shfl_up_sync(KP_FULL, xa, o);
+        uint32_t yb = __shfl_up_sync(KP_FULL, xb, o);
+        if (lane_id() >= (uint32_t)o) {
+            xa += ya;
+            xb += yb;
+        }
+    }
+    if (lane_id() == 31) {
+        wsa[threadIdx.x >> 5] = xa;
+        wsb[threadIdx.x >> 5] = xb;
+    }
+    __syncthreads();
+    uint32_t oa = (uint32_t)tmp[blockIdx.x], ob = TWO ? (uint32_t)tmp[ntiles + blockIdx.x] : 0;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) {
+        oa += wsa[w];
+        ob += wsb[w];
+    }
+    oa += xa - sa;
+    ob += xb - sb;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        uint32_t i = base + k;
+        if (i < n) {
+            out_a[i] = oa;
+            oa += va[k];
+            if (TWO) {
+                out_b[i] = ob;
+                ob += vb[k];
+            }
+        }
+    }
+}
+
+template <bool TWO>
+static int kp_scan_impl(const uint32_t* a, const uint32_t* b, uint32_t* oa, uint32_t* ob, uint32_t n, uint64_t* tmp,
+                        uint64_t* ta, uint64_t* tb, cudaStream_t st) {
+    uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (ntiles == 0) ntiles = 1;   // n == 0: still writes out[0] = 0 and the totals
+    kp_scan_tile_sums<TWO><<<ntiles, SCAN_THREADS, 0, st>>>(a, b, n, tmp, ntiles);
+    kp_scan_partials<TWO><<<1, 1024, 0, st>>>(tmp, ntiles, oa, ob, n, ta, tb);
+    kp_scan_apply<TWO><<<ntiles, SCAN_THREADS, 0, st>>>(a, b, n, tmp, ntiles, oa, ob);
+    int rc = kp_launch_check("kp_scan");
+    return rc < 0 ? rc : 3;
+}
+
+int kp_launch_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint64_t* tmp, uint64_t* total, cudaStream_t st) {
+    return kp_scan_impl<false>(in, nullptr, out, nullptr, n, tmp, total, nullptr, st);
+}
+int kp_launch_scan2(const uint32_t* a, const uint32_t* b, uint32_t* oa, uint32_t* ob, uint32_t n, uint64_t* tmp,
+                    uint64_t* ta, uint64_t* tb, cudaStream_t st) {
+    return kp_scan_impl<true>(a, b, oa, ob, n, tmp, ta, tb, st);
+}
+
+// =================================================================================================
+// Prep: UTF-8 validation + chars per sentence; then per-boundary info.  One warp per sentence.
+// =================================================================================================
+constexpr int PREP_THREADS = 256;
+
+__device__ __forceinline__ bool is_cont(uint32_t c) { return (c & 0xC0u) == 0x80u; }
+__device__ __forceinline__ uint32_t lead_len(uint32_t c) {  // 0 = not a valid lead byte
+    if (c < 0x80u) return 1;
+    if (c >= 0xC2u && c <= 0xDFu) return 2;
+    if (c >= 0xE0u && c <= 0xEFu) return 3;
+    if (c >= 0xF0u && c <= 0xF4u) return 4;
+    return 0;
+}
+
+// Rust's &str is valid UTF-8 by construction (src/tokenizer.rs:16 takes &str); the C ABI has to check.
+__global__ void __launch_bounds__(PREP_THREADS) kp_prep_count(const uint8_t* __restrict__ text,
+                                                              const uint64_t* __restrict__ off, uint64_t base,
+                                                              uint32_t S, uint32_t B, uint32_t* __restrict__ nchar,
+                                                              uint32_t* __restrict__ err) {
+    uint32_t s = (blockIdx.x * PREP_THREADS + threadIdx.x) >> 5;
+    if (s >= S) return;
+    uint64_t lo64 = off[s] - base, hi64 = off[s + 1] - base;
+    if (off[s] < base || hi64 < lo64 || hi64 > B) {
+        if (lane_id() == 0) {
+            atomicOr(&err[1], 1u);
+            nchar[s] = 0;
+        }
+        return;
+    }
+    uint32_t lo = (uint32_t)lo64, hi = (uint32_t)hi64;
+    uint32_t cnt = 0;
+    bool bad = false;
+    for (uint32_t i = lo + lane_id(); i < hi; i += 32) {
+        uint32_t c = text[i];
+        if (!is_cont(c)) {
+            cnt++;
+            uint32_t L = lead_len(c);
+            if (L == 0 || i + L > hi) {
+                bad = true;
+            } else if (L > 1) {
+                uint32_t c1 = text[i + 1];
+                uint32_t lo1 = 0x80u, hi1 = 0xBFu;
+                if (c == 0xE0u) lo1 = 0xA0u;
+                if (c == 0xEDu) hi1 = 0x9Fu;
+                if (c == 0xF0u) lo1 = 0x90u;
+                if (c == 0xF4u) hi1 = 0x8Fu;
+                if (c1 < lo1 || c1 > hi1) bad = true;
+                for (uint32_t k = 2; k < L; k++)
+                    if (!is_cont(text[i + k])) bad = true;
+            }
+        } else {
+            // a continuation byte must be claimed by a lead byte at distance d < its length
+            bool ok = false;
+            for (uint32_t d = 1; d <= 3 && i >= lo + d; d++) {
+                uint32_t p = text[i - d];
+                if (!is_cont(p)) {
+                    ok = lead_len(p) > d;
+                    break;
+                }
+            }
+            if (!ok) bad = true;
+        }
+    }
+    cnt = __reduce_add_sync(KP_FULL, cnt);
+    if (__any_sync(KP_FULL, bad) && lane_id() == 0) atomicOr(&err[0], 1u);
+    if (lane_id() == 0) nchar[s] = cnt;
+}
+
+__global__ void __launch_bounds__(PREP_THREADS) kp_prep_fill(const uint8_t* __restrict__ text,
+                                                             const uint64_t* __restrict__ off, uint64_t base, uint32_t S,
+                                                             const uint32_t* __restrict__ coff, kp_ddict d,
+                                                             uint4* __restrict__ binfo, uint32_t* __restrict__ bcount) {
+    uint32_t s = (blockIdx.x * PREP_THREADS + threadIdx.x) >> 5;
+    if (s >= S) return;
+    const uint32_t lane = lane_id();
+    const uint32_t lo = (uint32_t)(off[s] - base), hi = (uint32_t)(off[s + 1] - base);
+    const uint32_t bb = coff[s] + s;              // first boundary of this sentence
+    const uint32_t n = coff[s + 1] - coff[s];     // chars
+    // forward: byte offset + class of every char (Lattice::build's chars().enumerate(), lattice.rs:105)
+    uint32_t run = 0;
+    for (uint32_t i0 = lo; i0 < hi; i0 += 32) {
+        uint32_t i = i0 + lane;
+        uint32_t c = i < hi ? text[i] : 0x80u;
+        bool st = !is_cont(c);
+        uint32_t m = __ballot_sync(KP_FULL, st);
+        if (st) {
+            uint32_t cp;
+            if (c < 0x80u) cp = c;
+            else if (c < 0xE0u) cp = ((c & 0x1Fu) << 6) | (text[i + 1] & 0x3Fu);
+            else if (c < 0xF0u) cp = ((c & 0x0Fu) << 12) | ((text[i + 1] & 0x3Fu) << 6) | (text[i + 2] & 0x3Fu);
+            else cp = ((c & 0x07u) << 18) | ((text[i + 1] & 0x3Fu) << 12) | ((text[i + 2] & 0x3Fu) << 6) | (text[i + 3] & 0x3Fu);
+            // CharCategoryDef::char_category: out-of-table code points use entry 0 (char_category_def.rs:33-38)
+            uint32_t cat = d.cat[cp < d.n_cat ? cp : 0];
+            uint32_t p = run + __popc(m & lanemask_lt());
+            binfo[bb + p] = make_uint4(i, hi, 0u, cat);
+            bcount[bb + p] = p == 0 ? 1u : 0u;    // BOS sits in edges[0] (lattice.rs:156-164)
+        }
+        run += __popc(m);
+    }
+    if (lane == 0) {
+        binfo[bb + n] = make_uint4(hi, hi, bb + n + 1, 0xFFFFu);   // EOS boundary (lattice.rs:165-175)
+        bcount[bb + n] = n == 0 ? 1u : 0u;
+    }
+    __syncwarp();
+    // backward: end of the same-class run each char belongs to (lattice.rs:69-84), capped at 1024 chars
+    uint32_t carry = n;
+    for (int32_t k = (int32_t)((n + 31) / 32) - 1; k >= 0; k--) {
+        uint32_t p = (uint32_t)k * 32 + lane;
+        bool valid = p < n;
+        uint32_t cat = valid ? binfo[bb + p].w : 0xFFFEu;
+        uint32_t catn = (p + 1 < n) ? binfo[bb + p + 1].w : 0xFFFDu;
+        bool last = valid && cat != catn;
+        uint32_t m = __ballot_sync(KP_FULL, last);
+        uint32_t mge = m & ~lanemask_lt();
+        uint32_t runend = mge ? (uint32_t)k * 32 + (uint32_t)__ffs(mge) : carry;   // boundary after the run's last char
+        carry = __shfl_sync(KP_FULL, runend, 0);
+        if (valid) {
+            bool group = (d.catinfo[cat].flags & 2u) != 0;
+            uint32_t uend = group ? min(runend, p + KP_MAX_UNKNOWN_LEN) : p + 1;
+            binfo[bb + p].z = bb + uend;
+        }
+    }
+}
+
+int kp_launch_prep_count(const kp_chunk& c, cudaStream_t st) {
+    if (c.S == 0) return 0;
+    uint32_t blocks = (uint32_t)(((uint64_t)c.S * 32 + PREP_THREADS - 1) / PREP_THREADS);
+    kp_prep_count<<<blocks, PREP_THREADS, 0, st>>>(c.text, c.off, c.base, c.S, c.B, c.nchar, c.err);
+    return kp_launch_check("kp_prep_count");
+}
+
+int kp_launch_prep_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
+    if (c.S == 0) return 0;
+    uint32_t blocks = (uint32_t)(((uint64_t)c.S * 32 + PREP_THREADS - 1) / PREP_THREADS);
+    kp_prep_fill<<<blocks, PREP_THREADS, 0, st>>>(c.text, c.off, c.base, c.S, c.coff, d, c.binfo, c.bcount);
+    return kp_launch_check("kp_prep_fill");
+}
+
+// =================================================================================================
+// Lattice build: one thread per boundary walks the double array from that char to the end of the
+// sentence.  Pass 1 counts nodes per start boundary and per end boundary; pass 2 (after the scans)
+// writes the node records in the reference's insertion order.
+// =================================================================================================
+constexpr int LAT_THREADS = 256;
+
+template <bool FILL, bool WORK>
+__global__ void __launch_bounds__(LAT_THREADS) kp_lattice_walk(const uint8_t* __restrict__ text,
+                                                          const uint4* __restrict__ binfo, uint32_t NB, kp_ddict d,
+                                                          uint32_t* __restrict__ ncount, uint32_t* __restrict__ bcount,
+                                                          const uint32_t* __restrict__ noff, uint4* __restrict__ rec,
+                                                          uint64_t* __restrict__ totals) {
+    uint32_t b = blockIdx.x * LAT_THREADS + threadIdx.x;
+    uint32_t probes = 0, probes_ok = 0;
+    if (b < NB) {
+        const uint4 bi = binfo[b];
+        const uint32_t bp = bi.x, send = bi.y;
+        uint32_t o = FILL ? noff[b] : 0;
+        uint32_t total = 0;
+        if (bp == send) {
+            // EOS: Dummy node with morph (0,0,0) (lattice.rs:165-175)
+            if (FILL) rec[o] = make_uint4((uint32_t)KP_CLASS_DUMMY << KP_KIND_SHIFT, b, 0u, 0u);
+            total = 1;
+        } else {
+            bool matched = false;
+            if (d.da_len > KP_ROOT_ID) {
+                int prev = KP_ROOT_ID;
+                int base = d.da[KP_ROOT_ID].x;
+                uint32_t nch = 0;
+                for (uint32_t i = bp; i < send; i++) {
+                    uint32_t c = text[i];
+                    nch += !is_cont(c);
+                    int q = base + (int)c;                                   // da.rs:160
+                    if (WORK) probes++;
+                    if ((uint32_t)q >= d.da_len) break;                      // Vec::get -> None (da.rs:161)
+                    int2 nq = d.da[q];
+                    if (nq.y != prev) break;                                 // da.rs:162-164
+                    if (WORK) probes_ok++;
+                    int ahead = nq.x;                                        // + TERMINATOR (0), da.rs:165
+                    if ((uint32_t)ahead < d.da_len) {
+                        int2 na = d.da[ahead];
+                        if (na.y == q && na.x < 0) {                         // da.rs:167-174
+                            uint32_t id = (uint32_t)(-na.x);
+                            uint32_t k = (uint32_t)d.dup[id] + 1;            // index.rs:46-51
+                            matched = true;
+                            if (!FILL) {
+                                total += k;
+                                atomicAdd(&bcount[b + nch], k);
+                            } else {
+                                for (uint32_t j = 0; j < k; j++) {
+                                    short4 m = d.morphs[id + j - 1];         // lattice.rs:182
+                                    rec[o++] = make_uint4((id + j) | ((uint32_t)KP_CLASS_KNOWN << KP_KIND_SHIFT), b,
+                                                          (uint32_t)(uint16_t)m.x | ((uint32_t)(uint16_t)m.y << 16),
+                                                          (uint32_t)(uint16_t)m.z | (nch << 16));
+                                }
+                            }
+                        }
+                    }
+                    prev = q;
+                    base = nq.x;
+                }
+            }
+            // unknown words (lattice.rs:42-99)
+            const kp_catinfo ci = d.catinfo[bi.w & 0xFFu];
+            if ((!matched || (ci.flags & 1u)) && ci.unk_count) {
+                if (!FILL) {
+                    total += ci.unk_count;
+                    atomicAdd(&bcount[bi.z], ci.unk_count);
+                } else {
+                    uint32_t ulen = bi.z - b;
+                    for (uint32_t j = 0; j < ci.unk_count; j++) {
+                        short4 m = d.unk_morphs[ci.unk_first + j - 1];       // lattice.rs:195
+                        rec[o++] = make_uint4((uint32_t)(ci.unk_first + j) | ((uint32_t)KP_CLASS_UNKNOWN << KP_KIND_SHIFT),
+                                              b, (uint32_t)(uint16_t)m.x | ((uint32_t)(uint16_t)m.y << 16),
+                                              (uint32_t)(uint16_t)m.z | (ulen << 16));
+                    }
+                }
+            }
+        }
+        if (!FILL) ncount[b] = total;
+    }
+    if (WORK) {
+        probes = __reduce_add_sync(KP_FULL, probes);
+        probes_ok = __reduce_add_sync(KP_FULL, probes_ok);
+        if (lane_id() == 0) {
+            atomicAdd((unsigned long long*)&totals[4], (unsigned long long)probes);
+            atomicAdd((unsigned long long*)&totals[5], (unsigned long long)probes_ok);
+        }
+    }
+}
+
+int kp_launch_lattice_count(const kp_chunk& c, const kp_ddict& d, bool count_work, cudaStream_t st) {
+    if (c.NB == 0) return 0;
+    uint32_t blocks = (c.NB + LAT_THREADS - 1) / LAT_THREADS;
+    if (count_work)
+        kp_lattice_walk<false, true><<<blocks, LAT_THREADS, 0, st>>>(c.text, c.binfo, c.NB, d, c.ncount, c.bcount, nullptr,
+                                                                nullptr, c.totals);
+    else
+        kp_lattice_walk<false, false><<<blocks, LAT_THREADS, 0, st>>>(c.text, c.binfo, c.NB, d, c.ncount, c.bcount, nullptr,
+                                                                 nullptr, c.totals);
+    return kp_launch_check("kp_lattice_walk<count>");
+}
+
+int kp_launch_lattice_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
+    if (c.NB == 0) return 0;
+    uint32_t blocks = (c.NB + LAT_THREADS - 1) / LAT_THREADS;
+    kp_lattice_walk<true, false><<<blocks, LAT_THREADS, 0, st>>>(c.text, c.binfo, c.NB, d, nullptr, nullptr, c.noff, c.rec,
+                                                            c.totals);
+    return kp_launch_check("kp_lattice_walk<fill>");
+}
+
+// =================================================================================================
+// Bucketize: stable placement of every node into its end bucket (the reference's edges[end] lists,
+// ascending node index).  One warp per sentence walks its nodes in order, 32 at a time.
+// =================================================================================================
+constexpr int SENT_THREADS = 128;   // 4 sentences per CTA
+
+__global__ void __launch_bounds__(SENT_THREADS) kp_bucketize(uint32_t S, const uint32_t* __restrict__ coff,
+                                                             const uint32_t* __restrict__ noff,
+                                                             const uint32_t* __restrict__ boff,
+                                                             const uint4* __restrict__ rec, uint32_t* __restrict__ bfill,
+                                                             uint32_t* __restrict__ slot, int16_t* __restrict__ bright,
+                                                             uint32_t* __restrict__ bnode, int32_t* __restrict__ bdp) {
+    uint32_t s = (blockIdx.x * SENT_THREADS + threadIdx.x) >> 5;
+    if (s >= S) return;
+    const uint32_t lane = lane_id();
+    const uint32_t bb = coff[s] + s, n = coff[s + 1] - coff[s];
+    const uint32_t n0 = noff[bb], n1 = noff[bb + n];   // nodes before the EOS node (which is node n1)
+    if (lane == 0) {
+        uint32_t q = boff[bb];                          // BOS: dp None -> unwrap_or(0) (lattice.rs:127)
+        bright[q] = 0;
+        bnode[q] = KP_NONE;
+        bdp[q] = 0;
+    }
+    for (uint32_t i0 = n0; i0 < n1; i0 += 32) {
+        uint32_t i = i0 + lane;
+        bool valid = i < n1;
+        uint4 r = valid ? rec[i] : make_uint4(0, 0, 0, 0);
+        uint32_t e = valid ? r.y + (r.w >> 16) : KP_NONE;   // end boundary = start + char_len (lattice.rs:187,200)
+        uint32_t m = __match_any_sync(KP_FULL, e);
+        uint32_t leader = (uint32_t)__ffs(m) - 1;
+        uint32_t old = 0;
+        if (valid && lane == leader) {
+            old = bfill[e];
+            bfill[e] = old + (uint32_t)__popc(m);
+        }
+        old = __shfl_sync(KP_FULL, old, leader);
+        if (valid) {
+            uint32_t q = boff[e] + old + (uint32_t)__popc(m & lanemask_lt()) + (e == bb ? 1u : 0u);
+            slot[i] = q;
+            bright[q] = (int16_t)(r.z >> 16);
+            bnode[q] = i;
+        }
+        __syncwarp();
+    }
+}
+
+int kp_launch_bucketize(const kp_chunk& c, cudaStream_t st) {
+    if (c.S == 0) return 0;
+    uint32_t blocks = (uint32_t)(((uint64_t)c.S * 32 + SENT_THREADS - 1) / SENT_THREADS);
+    kp_bucketize<<<blocks, SENT_THREADS, 0, st>>>(c.S, c.coff, c.noff, c.boff, c.rec, c.bfill, c.slot, c.bright, c.bnode,
+                                                  c.bdp);
+    return kp_launch_check("kp_bucketize");
+}
+
+// =================================================================================================
+// Viterbi forward sweep: one warp per sentence, boundary by boundary.  Lanes hold the nodes ENDING
+// at the boundary (dp, right_id); for every node STARTING there the lanes gather
+// conn[left*row + right] and a warp min-reduction picks the first minimal predecessor.
+//   total = min(dp[j] + cost_i + conn(right_j, left_i), INF); strict '<' from INF  (lattice.rs:121-141)
+// =================================================================================================
+__global__ void __launch_bounds__(SENT_THREADS) kp_viterbi(uint32_t S, const uint32_t* __restrict__ coff,
+                                                           const uint32_t* __restrict__ noff,
+                                                           const uint32_t* __restrict__ boff,
+                                                           const uint4* __restrict__ rec,
+                                                           const uint32_t* __restrict__ slot,
+                                                           const int16_t* __restrict__ bright, int32_t* bdp,
+                                                           uint32_t* __restrict__ pre, int32_t* __restrict__ eos_cost,
+                                                           const int16_t* __restrict__ conn, uint32_t conn_row) {
+    uint32_t s = (blockIdx.x * SENT_THREADS + threadIdx.x) >> 5;
+    if (s >= S) return;
+    const uint32_t lane = lane_id();
+    const uint32_t bb = coff[s] + s, n = coff[s + 1] - coff[s];
+    uint32_t t0 = noff[bb], q0 = boff[bb];
+    for (uint32_t p = 0; p <= n; p++) {
+        const uint32_t b = bb + p;
+        const uint32_t t1 = noff[b + 1], q1 = boff[b + 1];
+        const uint32_t np = q1 - q0;
+        for (uint32_t tc = t0; tc < t1; tc += 32) {
+            const uint32_t i = tc + lane;
+            const bool tvalid = i < t1;
+            uint4 r = tvalid ? rec[i] : make_uint4(0, 0, 0, 0);
+            const uint32_t left_off = (r.z & 0xFFFFu) * conn_row;
+            const int cost = (int)(int16_t)(r.w & 0xFFFFu);
+            int best = INT_MAX;
+            uint32_t arg = KP_NONE;
+            const uint32_t ntc = min(32u, t1 - tc);
+            for (uint32_t pc = q0; pc < q1; pc += 32) {
+                const uint32_t j = pc + lane;
+                const bool pvalid = j < q1;
+                const int dpj = pvalid ? bdp[j] : 0;
+                const uint32_t rj = pvalid ? (uint32_t)(uint16_t)bright[j] : 0u;
+                for (uint32_t t = 0; t < ntc; t++) {
+                    uint32_t lo = __shfl_sync(KP_FULL, left_off, t);
+                    int v = pvalid ? dpj + (int)conn[lo + rj] : INT_MAX;     // connection.rs:12-14
+                    int m = __reduce_min_sync(KP_FULL, v);
+                    uint32_t first = (uint32_t)__ffs(__ballot_sync(KP_FULL, v == m)) - 1;
+                    if (lane == t && m < best) {     // strict: the first minimum wins (lattice.rs:136)
+                        best = m;
+                        arg = pc + first;
+                    }
+                }
+            }
+            if (tvalid) {
+                int dp = KP_INF;
+                uint32_t pr = KP_NONE;
+                if (np != 0 && best != INT_MAX) {
+                    int total = best + cost;
+                    if (total < KP_INF) {
+                        dp = total;
+                        pr = arg;
+                    }
+                }
+                pre[i] = pr;
+                if ((r.x >> KP_KIND_SHIFT) == KP_CLASS_DUMMY) eos_cost[s] = dp;
+                else bdp[slot[i]] = dp;
+            }
+        }
+        __syncwarp();
+        t0 = t1;
+        q0 = q1;
+    }
+}
+
+int kp_launch_viterbi(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
+    if (c.S == 0) return 0;
+    uint32_t blocks = (uint32_t)(((uint64_t)c.S * 32 + SENT_THREADS - 1) / SENT_THREADS);
+    kp_viterbi<<<blocks, SENT_THREADS, 0, st>>>(c.S, c.coff, c.noff, c.boff, c.rec, c.slot, c.bright, c.bdp, c.pre,
+                                                c.eos_cost, d.conn, d.conn_row);
+    return kp_launch_check("kp_viterbi");
+}
+
+// E = sum over boundaries of (#targets x #predecessors): the pairs visited by lattice.rs:122-125
+__global__ void __launch_bounds__(256) kp_pair_count(uint32_t NB, const uint32_t* __restrict__ noff,
+                                                     const uint32_t* __restrict__ boff, uint64_t* __restrict__ totals) {
+    uint32_t b = blockIdx.x * 256 + threadIdx.x;
+    unsigned long long e = 0;
+    if (b < NB) e = (unsigned long long)(noff[b + 1] - noff[b]) * (boff[b + 1] - boff[b]);
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(KP_FULL, e, o);
+    if (lane_id() == 0 && e) atomicAdd((unsigned long long*)&totals[6], e);
+}
+
+int kp_launch_pair_count(const kp_chunk& c, cudaStream_t st) {
+    if (c.NB == 0) return 0;
+    kp_pair_count<<<(c.NB + 255) / 256, 256, 0, st>>>(c.NB, c.noff, c.boff, c.totals);
+    return kp_launch_check("kp_pair_count");
+}
+
+// =================================================================================================
+// Back-trace (lattice.rs:144-153) + Node -> Token (tokenizer.rs:22-43).  One thread per sentence:
+// pass 1 counts the path, pass 2 (after the scan) writes it front to back.
+// =================================================================================================
+template <bool WRITE>
+__global__ void __launch_bounds__(128) kp_backtrace(uint32_t S, const uint32_t* __restrict__ coff,
+                                                    const uint32_t* __restrict__ noff, const uint4* __restrict__ rec,
+                                                    const uint32_t* __restrict__ pre, const uint32_t* __restrict__ bnode,
+                                                    const uint4* __restrict__ binfo, uint32_t* __restrict__ tcount,
+                                                    const uint32_t* __restrict__ toff, uint64_t tok_base,
+                                                    uint64_t* __restrict__ tok_off, kp_token* __restrict__ tokens) {
+    uint32_t s = blockIdx.x * 128 + threadIdx.x;
+    if (s > S) return;
+    if (WRITE) tok_off[s] = tok_base + toff[s];
+    if (s == S) return;
+    const uint32_t bb = coff[s] + s, n = coff[s + 1] - coff[s];
+    uint32_t cur = noff[bb + n];                 // `self.nodes.len() - 1`: the EOS node
+    const uint32_t sent_byte0 = binfo[bb].x;     // for n == 0 this is the EOS boundary: also the sentence start
+    uint32_t cnt = 0;
+    uint32_t w = WRITE ? toff[s + 1] : 0;        // one past this sentence's last token
+    while (true) {
+        uint32_t q = pre[cur];
+        if (q == KP_NONE) break;                 // `while let Some(pre) = pre_nodes[pos]`
+        if (WRITE) {
+            uint4 r = rec[cur];
+            uint32_t kind = r.x >> KP_KIND_SHIFT;
+            kp_token t;
+            t.id = (int32_t)(r.x & KP_ID_MASK);
+            t.position = binfo[r.y].x - sent_byte0;
+            t.start = r.y - bb;
+            t.char_len = kind == KP_CLASS_DUMMY ? 3 : (uint16_t)(r.w >> 16);   // "EOS".chars().count()
+            t.cls = (uint8_t)kind;
+            t.reserved = 0;
+            tokens[--w] = t;
+        }
+        cnt++;
+        cur = bnode[q];
+        if (cur == KP_NONE) break;               // reached BOS, which has no predecessor and is not emitted
+    }
+    if (!WRITE) tcount[s] = cnt;
+}
+
+int kp_launch_backtrace_count(const kp_chunk& c, cudaStream_t st) {
+    kp_backtrace<false><<<(c.S + 1 + 127) / 128, 128, 0, st>>>(c.S, c.coff, c.noff, c.rec, c.pre, c.bnode, c.binfo,
+                                                               c.tcount, nullptr, 0, nullptr, nullptr);
+    return kp_launch_check("kp_backtrace<count>");
+}
+
+int kp_launch_backtrace_write(const kp_chunk& c, uint64_t tok_base, cudaStream_t st) {
+    kp_backtrace<true><<<(c.S + 1 + 127) / 128, 128, 0, st>>>(c.S, c.coff, c.noff, c.rec, c.pre, c.bnode, c.binfo,
+                                                              nullptr, c.toff32, tok_base, c.tok_off, c.tokens);
+    return kp_launch_check("kp_backtrace<write>");
+}
+
+// =================================================================================================
+// Single-query common-prefix search (parity tests of the reference's da.rs / index.rs vectors).
+// =================================================================================================
+__global__ void kp_common_prefix(kp_ddict d, const uint8_t* __restrict__ text, uint32_t len, int expand_dup,
+                                 int64_t* __restrict__ ids, uint64_t* __restrict__ lens, uint32_t cap,
+                                 uint32_t* __restrict__ n_out) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint32_t n = 0;
+    if (d.da_len > KP_ROOT_ID) {
+        int prev = KP_ROOT_ID, base = d.da[KP_ROOT_ID].x;
+        for (uint32_t i = 0; i < len; i++) {
+            int q = base + (int)text[i];
+            if ((uint32_t)q >= d.da_len) break;
+            int2 nq = d.da[q];
+            if (nq.y != prev) break;
+            int ahead = nq.x;
+            if ((uint32_t)ahead < d.da_len) {
+                int2 na = d.da[ahead];
+                if (na.y == q && na.x < 0) {
+                    uint32_t id = (uint32_t)(-na.x);
+                    uint32_t k = expand_dup ? (uint32_t)d.dup[id] + 1 : 1;
+                    for (uint32_t j = 0; j < k; j++) {
+                        if (n < cap) {
+                            ids[n] = (int64_t)id + j;
+                            lens[n] = (uint64_t)i + 1;
+                        }
+                        n++;
+                    }
+                }
+            }
+            prev = q;
+            base = nq.x;
+        }
+    }
+    *n_out = n;
+}
+
+int kp_launch_common_prefix(const kp_ddict& d, const uint8_t* d_text, uint32_t len, int expand_dup, int64_t* d_ids,
+                            uint64_t* d_lens, uint32_t cap, uint32_t* d_n, cudaStream_t st) {
+    kp_common_prefix<<<1, 32, 0, st>>>(d, d_text, len, expand_dup, d_ids, d_lens, cap, d_n);
+    return kp_launch_check("kp_common_prefix");
+}

@@ -1,0 +1,56 @@
+// kp_kernels.cuh — launch wrappers of the sm_100a kernels (definitions in kp_kernels.cu).
+//
+// Device data layout of one chunk (S sentences, B bytes, C chars, NB = C + S boundaries, N nodes):
+//   text    u8 [B]        input bytes (chunk-relative)
+//   off     u64[S+1]      caller's sentence offsets (absolute; `base` = offset of the chunk's first byte)
+//   coff    u32[S+1]      exclusive scan of chars per sentence; boundary base of sentence s = coff[s] + s
+//   binfo   uint4[NB]     per boundary {byte offset, sentence end byte, unknown-word end boundary, class}
+//                         boundary p of a sentence = position before char p; p = n_chars is the EOS boundary
+//   ncount/noff u32[NB+1] nodes STARTING at each boundary (count / exclusive scan) = reference insertion order
+//   bcount/boff u32[NB+1] nodes ENDING at each boundary (+BOS at p=0)  = the reference's `edges` buckets
+//   rec     uint4[N]      node {id|class<<30, start boundary, left|right<<16, cost|char_len<<16}
+//   slot    u32[N]        position of the node in its end bucket (global index into the b* arrays)
+//   bright  i16[N], bnode u32[N], bdp i32[N]   per bucket entry: right_id, node index, dp value
+//   pre     u32[N]        predecessor as a bucket slot (KP_NONE = Option::None)
+#pragma once
+#include "kp_common.cuh"
+
+struct kp_chunk {
+    // inputs
+    const uint8_t* text;     // device, chunk-relative base
+    const uint64_t* off;     // device, [S+1]
+    uint64_t base;           // off[0]
+    uint32_t S, B;
+    // sizes learnt on the way
+    uint32_t C, NB, N;
+    // scratch (device)
+    uint32_t* nchar;  uint32_t* coff;
+    uint4* binfo;
+    uint32_t* ncount; uint32_t* noff; uint32_t* bcount; uint32_t* boff; uint32_t* bfill;
+    uint4* rec; uint32_t* slot; int16_t* bright; uint32_t* bnode; int32_t* bdp; uint32_t* pre;
+    int32_t* eos_cost; uint32_t* tcount; uint32_t* toff32;
+    uint64_t* tok_off;       // [S+1] output (rebased by tok_base)
+    kp_token* tokens;        // output
+    uint64_t* scan_tmp;      // tile partials for the scans
+    uint64_t* totals;        // [8] device scalars: 0 chars, 1 nodes, 2 bucket entries, 3 tokens, 4 P, 5 P_ok, 6 E
+    uint32_t* err;           // [2] device flags: 0 utf8, 1 offsets
+};
+
+uint32_t kp_scan_tmp_elems(uint32_t n);   // uint64 elements of scan_tmp needed for an n-element scan
+
+// each returns the number of kernels launched (negative kp_status on launch failure)
+int kp_launch_prep_count(const kp_chunk& c, cudaStream_t st);
+int kp_launch_prep_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
+int kp_launch_lattice_count(const kp_chunk& c, const kp_ddict& d, bool count_work, cudaStream_t st);
+int kp_launch_lattice_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
+int kp_launch_bucketize(const kp_chunk& c, cudaStream_t st);
+int kp_launch_viterbi(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
+int kp_launch_pair_count(const kp_chunk& c, cudaStream_t st);
+int kp_launch_backtrace_count(const kp_chunk& c, cudaStream_t st);
+int kp_launch_backtrace_write(const kp_chunk& c, uint64_t tok_base, cudaStream_t st);
+// exclusive scans, n inputs -> n+1 outputs; total (u64) written to *total
+int kp_launch_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint64_t* tmp, uint64_t* total, cudaStream_t st);
+int kp_launch_scan2(const uint32_t* in_a, const uint32_t* in_b, uint32_t* out_a, uint32_t* out_b, uint32_t n,
+                    uint64_t* tmp, uint64_t* total_a, uint64_t* total_b, cudaStream_t st);
+int kp_launch_common_prefix(const kp_ddict& d, const uint8_t* d_text, uint32_t len, int expand_dup, int64_t* d_ids,
+                            uint64_t* d_lens, uint32_t cap, uint32_t* d_n, cudaStream_t st);

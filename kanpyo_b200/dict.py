@@ -1,0 +1,115 @@
+"""Dict — the hot-path members of the reference's `kanpyo_dict::dict::Dict` (kanpyo-dict/src/dict.rs:21-30)
+as flat little-endian numpy arrays, plus the staging of those arrays to HBM through the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+
+
+@dataclass
+class Dict:
+    da: np.ndarray                 # int32 [da_len, 2] (base, check)            trie/da.rs:14-20
+    dup_ids: np.ndarray            # int64 [n_dup]                               index.rs:12
+    dup_counts: np.ndarray         # uint64 [n_dup]
+    morphs: np.ndarray             # int16 [n, 3] (left_id, right_id, cost)      morph.rs:7-11
+    conn_row: int                  # connection.rs:5-9
+    conn_col: int
+    conn: np.ndarray               # int16 [row*col]
+    char_category: np.ndarray      # uint8 [65536]                               char_category_def.rs:15-20
+    invoke_list: np.ndarray        # uint8 (bool)
+    group_list: np.ndarray         # uint8 (bool)
+    unk_cat: np.ndarray            # uint8 [n_map]                               unk_dict.rs:12-16
+    unk_first_id: np.ndarray       # int64 [n_map]
+    unk_count: np.ndarray          # uint64 [n_map]
+    unk_morphs: np.ndarray         # int16 [n_unk, 3]
+    # not read by the hot path
+    char_class: list = field(default_factory=list)
+    keywords: list = field(default_factory=list)        # sorted surfaces incl. duplicates (bytes)
+    features: tuple = field(default_factory=tuple)      # (rows, names)   morph_feature.rs:7-10
+    unk_features: tuple = field(default_factory=tuple)
+
+    _handle: object = field(default=None, repr=False, compare=False)
+    _device: int = field(default=-1, repr=False, compare=False)
+
+    # ---- C ABI ---------------------------------------------------------------------------------
+    def _arrays(self):
+        c = np.ascontiguousarray
+        keep = dict(
+            da=c(self.da, np.int32), dup_ids=c(self.dup_ids, np.int64), dup_counts=c(self.dup_counts, np.uint64),
+            morphs=c(self.morphs, np.int16), conn=c(self.conn, np.int16), cat=c(self.char_category, np.uint8),
+            invoke=c(self.invoke_list, np.uint8), group=c(self.group_list, np.uint8), ucat=c(self.unk_cat, np.uint8),
+            ufirst=c(self.unk_first_id, np.int64), ucount=c(self.unk_count, np.uint64),
+            umorphs=c(self.unk_morphs, np.int16))
+        p = lambda a: a.ctypes.data_as(C.c_void_p) if a.size else None
+        a = _lib.DictArrays(
+            da=p(keep["da"]), da_len=keep["da"].size // 2,
+            dup_ids=p(keep["dup_ids"]), dup_counts=p(keep["dup_counts"]), n_dup=keep["dup_ids"].size,
+            morphs=p(keep["morphs"]), n_morphs=keep["morphs"].size // 3,
+            conn_row=int(self.conn_row), conn_col=int(self.conn_col), conn=p(keep["conn"]),
+            char_category=p(keep["cat"]), n_char_category=keep["cat"].size,
+            invoke_list=p(keep["invoke"]), n_invoke=keep["invoke"].size,
+            group_list=p(keep["group"]), n_group=keep["group"].size,
+            unk_cat=p(keep["ucat"]), unk_first_id=p(keep["ufirst"]), unk_count=p(keep["ucount"]),
+            n_unk_map=keep["ucat"].size,
+            unk_morphs=p(keep["umorphs"]), n_unk_morphs=keep["umorphs"].size // 3)
+        if keep["conn"].size != int(self.conn_row) * int(self.conn_col):
+            raise ValueError("conn has %d entries, expected %d x %d" % (keep["conn"].size, self.conn_row, self.conn_col))
+        return a, keep
+
+    def pack(self) -> np.ndarray:
+        """Validated packed blob (host only; what rank 0 broadcasts to the other GPUs)."""
+        L = _lib.load()
+        a, _keep = self._arrays()
+        size = C.c_uint64()
+        _lib.check(L.kp_dict_pack(C.byref(a), None, 0, C.byref(size)))
+        blob = np.empty(size.value, np.uint8)
+        _lib.check(L.kp_dict_pack(C.byref(a), blob.ctypes.data_as(C.c_void_p), size.value, C.byref(size)))
+        return blob
+
+    def device_handle(self, device: int = 0):
+        """kp_dict* staged on `device` (created once per Dict and device)."""
+        if self._handle is None or self._device != device:
+            self.close()
+            L = _lib.load()
+            a, _keep = self._arrays()
+            h = C.c_void_p()
+            _lib.check(L.kp_dict_create(C.byref(a), device, C.byref(h)))
+            self._handle, self._device = h, device
+        return self._handle
+
+    def close(self):
+        if self._handle is not None:
+            _lib.load().kp_dict_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- persistence of the flat form (a cache, not the reference's .dict zip) -------------------
+    _NPZ = ("da", "dup_ids", "dup_counts", "morphs", "conn", "char_category", "invoke_list", "group_list", "unk_cat",
+            "unk_first_id", "unk_count", "unk_morphs")
+
+    def save_npz(self, path: str):
+        kw_blob = np.frombuffer(b"".join(self.keywords), np.uint8)
+        kw_off = np.zeros(len(self.keywords) + 1, np.uint64)
+        if self.keywords:
+            kw_off[1:] = np.cumsum([len(k) for k in self.keywords], dtype=np.uint64)
+        np.savez(path, **{k: getattr(self, k) for k in self._NPZ},
+                 conn_shape=np.array([self.conn_row, self.conn_col], np.uint64),
+                 char_class=np.array(self.char_class if self.char_class else [""]), kw_blob=kw_blob, kw_off=kw_off)
+
+    @classmethod
+    def load_npz(cls, path: str) -> "Dict":
+        z = np.load(path, allow_pickle=False)
+        kw_blob = z["kw_blob"].tobytes()
+        kw_off = z["kw_off"]
+        keywords = [kw_blob[int(kw_off[i]):int(kw_off[i + 1])] for i in range(len(kw_off) - 1)]
+        return cls(**{k: z[k] for k in cls._NPZ}, conn_row=int(z["conn_shape"][0]), conn_col=int(z["conn_shape"][1]),
+                   char_class=[str(x) for x in z["char_class"]], keywords=keywords)

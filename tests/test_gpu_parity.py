@@ -1,0 +1,246 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle: bit-exact tokens (id, class, byte position,
+char start/end, surface bytes) and dp[EOS], plus node-level lattice parity.  Needs a GPU: -m gpu."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_batch_equal, pack, reference_fixture_dict, to_product_dict
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _check_sentences(gpu, orc, sentences):
+    text, off = pack(sentences)
+    res = gpu.tokenize_batch_bytes(text, off)
+    o_off, o_tok, o_cost, _ = orc.tokenize_batch(text, off)
+    assert_batch_equal(res, o_off, o_tok, o_cost)
+    return res
+
+
+# ---- the reference's own known-answer vectors, on the device trie ---------------------------------------
+def _small(oracle_mod, keywords, **kw):
+    import kanpyo_b200
+    od = oracle_mod.dict_from_keywords(keywords, **kw)
+    return kanpyo_b200.Tokenizer(to_product_dict(od), device=0), oracle_mod.OracleTokenizer(od)
+
+
+def test_da_search_common_prefix_vectors(oracle_mod):     # da.rs:289-323
+    kws = ["早稲田", "早稲田大学", "東京", "東京大学", "東京大学大学院", "東京大学大学院情報理工学研究科",
+           "東京大学大学院情報理工学研究科創造情報学専攻", "東京工業大学"]
+    g, _ = _small(oracle_mod, kws)
+    assert g.common_prefix("東京大学大学院情報理工学研究科創造情報学専攻", expand_dup=False) == [
+        (3, 6), (4, 12), (5, 21), (6, 45), (7, 66)]
+    assert g.common_prefix("早稲田大学", expand_dup=False) == [(1, 9), (2, 15)]
+    assert g.common_prefix("大学", expand_dup=False) is None
+
+
+def test_index_vectors(oracle_mod):                       # index.rs:98-150
+    g, _ = _small(oracle_mod, ["apple", "apple", "banana", "banana", "banana", "cherry"],
+                  morphs=np.zeros((6, 3), np.int16))
+    assert g.common_prefix("apple") == [(1, 5), (2, 5)]
+    assert g.common_prefix("banana") == [(3, 6), (4, 6), (5, 6)]
+    g, _ = _small(oracle_mod, ["apple", "banana"])
+    assert g.common_prefix("cherry") is None
+    g, _ = _small(oracle_mod, ["東京", "東京大学", "東京大学大学院"])
+    assert g.common_prefix("東京大学大学院情報学") == [(1, 6), (2, 12), (3, 21)]
+
+
+def test_exact_keys_found(oracle_mod):                    # da.rs:253-286, 326-351 via common-prefix hits
+    kws = sorted(["12345", "2345", "１２３", "abc", "ABCD", "あいう", "Ａ"], key=lambda s: s.encode("utf-8"))
+    g, o = _small(oracle_mod, kws)
+    for i, k in enumerate(kws):
+        hits = g.common_prefix(k, expand_dup=False)
+        assert hits is not None and hits[-1] == (i + 1, len(k.encode("utf-8")))
+        assert hits == o.common_prefix(k, use_dup=False)
+    for k in ["", "b", "あい"]:
+        assert g.common_prefix(k) == o.common_prefix(k)
+
+
+def test_empty_dictionary_is_graceful(oracle_mod):
+    """index.rs:92-95 builds an empty index; the reference would panic on search, the device path finds nothing."""
+    g, _ = _small(oracle_mod, [], unk_map={0: (1, 1)}, unk_morphs=[(0, 0, 7)])
+    assert g.common_prefix("anything") is None
+    toks = g.tokenize("ab")
+    assert [(t.id, int(t.cls), t.surface) for t in toks] == [(1, 2, "a"), (1, 2, "b"), (0, 0, "EOS")]
+
+
+# ---- src/tests.rs fixture --------------------------------------------------------------------------------
+def test_reference_fixture(oracle_mod):
+    import kanpyo_b200
+    from kanpyo_b200 import TokenClass
+    od = reference_fixture_dict(oracle_mod)
+    g = kanpyo_b200.Tokenizer(to_product_dict(od), device=0)
+    o = oracle_mod.OracleTokenizer(od)
+    toks, cost = g.tokenize_with_cost("テスト")
+    assert [(t.id, t.cls, t.position, t.start, t.end, t.surface) for t in toks] == [
+        (1, TokenClass.Known, 0, 0, 3, "テスト"), (0, TokenClass.Dummy, 9, 3, 6, "EOS")]
+    assert cost == 1000
+    toks, cost = g.tokenize_with_cost("")
+    assert [(t.id, t.cls, t.position, t.start, t.end, t.surface) for t in toks] == [(0, TokenClass.Dummy, 0, 0, 3, "EOS")]
+    assert cost == 0
+    toks, cost = g.tokenize_with_cost("あいうえお")
+    assert [(t.id, t.cls, t.position, t.start, t.end, t.surface) for t in toks] == [
+        (2, TokenClass.Unknown, 0, 0, 5, "あいうえお"), (0, TokenClass.Dummy, 15, 5, 8, "EOS")]
+    assert cost == 5200
+    _check_sentences(g, o, ["テスト", "", "あいうえお", "辞書テスト形態素", "テスト辞書あい形態素うえ", "xyz", "漢字テスト"])
+    # no unknown entry for DEFAULT: 'x' has no node at all, the path is cut (dead nodes, truncated back-trace)
+    for s in ["xテスト", "テストx", "xx", "テxスト"]:
+        _check_sentences(g, o, [s])
+
+
+# ---- IPADIC ----------------------------------------------------------------------------------------------
+def test_cfg1(gpu_tok, oracle_tok):
+    """BASELINE.json configs[0]."""
+    s = "すもももももももものうち"
+    toks, cost = gpu_tok.tokenize_with_cost(s)
+    otoks, ocost = oracle_tok.tokenize(s)
+    assert cost == ocost == 21245
+    assert [(t.id, int(t.cls), t.position, t.start, t.end, t.surface) for t in toks] == otoks
+    assert [t.surface for t in toks] == ["すもも", "も", "もも", "も", "もも", "の", "うち", "EOS"]
+
+
+def test_golden_sentences(gpu_tok):
+    g = json.load(open(os.path.join(GOLDEN, "ipadic_sentences.json"), encoding="utf-8"))
+    for s in g["sentences"]:
+        toks, cost = gpu_tok.tokenize_with_cost(s["text"])
+        assert cost == s["cost"], s["text"]
+        got = [[t.id, int(t.cls), t.position, t.start, t.end, t.surface] for t in toks]
+        assert got == [t[:6] for t in s["tokens"]], s["text"]
+    # and as one batch
+    res = gpu_tok.tokenize_batch([s["text"] for s in g["sentences"]])
+    for toks, s in zip(res, g["sentences"]):
+        assert [[t.id, int(t.cls), t.position, t.start, t.end, t.surface] for t in toks] == [t[:6] for t in s["tokens"]]
+
+
+def test_lattice_node_parity(gpu_tok, oracle_tok):
+    """Lattice{nodes} order + dp/pre of every node (lattice.rs:101-154), including dead nodes."""
+    for s in ["すもももももももものうち", "Tシャツを3枚買ったABC", "\U0001F600の犬", "", "カタカナカタカナ", "あ" * 40,
+              "東京都に住んでいます。"]:
+        la = gpu_tok.lattice(s)
+        ol = oracle_tok.lattice(s)
+        on = ol["nodes"]          # kind, id, byte_pos, char_pos, end_char_pos, left, right, cost, byte_len
+        assert len(la) == len(on), s
+        assert np.array_equal(la["cls"], on[:, 0]) and np.array_equal(la["id"], on[:, 1]), s
+        assert np.array_equal(la["byte_pos"], on[:, 2]) and np.array_equal(la["char_pos"], on[:, 3]), s
+        assert np.array_equal(la["end_char"], on[:, 4]), s
+        assert np.array_equal(la["left_id"], on[:, 5]) and np.array_equal(la["right_id"], on[:, 6]), s
+        assert np.array_equal(la["cost"], on[:, 7]), s
+        odp = np.where(ol["dp"] == np.iinfo(np.int64).min, np.iinfo(np.int32).min, ol["dp"])
+        assert np.array_equal(la["dp"].astype(np.int64), odp), s
+        assert np.array_equal(la["pre"].astype(np.int64), ol["pre"]), s
+
+
+@pytest.mark.parametrize("kind,n", [("cfg2", 4096), ("cfg3", 4096), ("cfg4", 24)])
+def test_corpus_parity(gpu_tok, oracle_tok, vocab, kind, n):
+    from kanpyo_b200 import corpus
+    text, off = corpus.synth_corpus(vocab, n, kind)
+    res = gpu_tok.tokenize_batch_bytes(text, off)
+    o_off, o_tok, o_cost, ctr = oracle_tok.tokenize_batch(text, off, threads=8)
+    assert_batch_equal(res, o_off, o_tok, o_cost)
+    c = gpu_tok.counters()
+    assert (c["bytes"], c["chars"], c["nodes"], c["tokens"]) == (ctr["B"], ctr["C"], ctr["N"], ctr["T"])
+
+
+def test_work_counters(gpu_tok, oracle_tok, vocab):
+    """P, P_ok, E of the counting kernels equal the oracle's exact counts (the roofline's inputs)."""
+    from kanpyo_b200 import corpus
+    text, off = corpus.synth_corpus(vocab, 1024, "cfg2")
+    gpu_tok.set_count_work(True)
+    try:
+        gpu_tok.tokenize_batch_bytes(text, off)
+        c = gpu_tok.counters()
+    finally:
+        gpu_tok.set_count_work(False)
+    _, _, _, ctr = oracle_tok.tokenize_batch(text, off, threads=8)
+    assert (c["probes"], c["probes_ok"], c["pairs"]) == (ctr["P"], ctr["P_ok"], ctr["E"])
+
+
+def test_golden_cfg2_checksum(gpu_tok, vocab):
+    import hashlib
+    from kanpyo_b200 import corpus
+    g = json.load(open(os.path.join(GOLDEN, "cfg2_512.json")))
+    text, off = corpus.synth_corpus(vocab, g["n_sent"], g["kind"], g["seed"])
+    res = gpu_tok.tokenize_batch_bytes(text, off)
+    t = res.tokens
+    packed = np.stack([t["id"].astype(np.int64), t["cls"].astype(np.int64), t["position"].astype(np.int64),
+                       t["start"].astype(np.int64), t["start"].astype(np.int64) + t["char_len"]], axis=1)
+    assert hashlib.sha256(np.ascontiguousarray(packed).tobytes()).hexdigest() == g["tokens_sha256"]
+    assert hashlib.sha256(np.ascontiguousarray(res.eos_cost).tobytes()).hexdigest() == g["cost_sha256"]
+
+
+def test_chunking_is_invisible(gpu_ipadic, oracle_tok, vocab):
+    """Small chunk size (many device passes) gives the same packed result as one pass."""
+    import kanpyo_b200
+    from kanpyo_b200 import corpus
+    text, off = corpus.synth_corpus(vocab, 600, "cfg2")
+    t = kanpyo_b200.Tokenizer(gpu_ipadic, device=0)
+    t.set_chunk_bytes(10_000)
+    res = t.tokenize_batch_bytes(text, off)
+    assert t.profile()["chunks"] > 5
+    o_off, o_tok, o_cost, _ = oracle_tok.tokenize_batch(text, off, threads=4)
+    assert_batch_equal(res, o_off, o_tok, o_cost)
+    t.close()
+
+
+def test_ragged_and_empty(gpu_tok, oracle_tok):
+    sents = ["", "", "あ", "", "犬" * 300, "", "a", ""]
+    _check_sentences(gpu_tok, oracle_tok, sents)
+    _check_sentences(gpu_tok, oracle_tok, [""])
+    res = gpu_tok.tokenize_batch_bytes(b"", np.zeros(1, np.uint64))
+    assert len(res.tokens) == 0 and res.tok_off.tolist() == [0]
+
+
+def test_long_unknown_runs(gpu_tok, oracle_tok):
+    """Unknown-word grouping cap of 1024 chars (lattice.rs:55,79-82) and buckets wider than a warp."""
+    sents = ["ー" * 1030, "ア" * 2100, "a" * 1500 + "犬" + "1" * 40, "ｱ" * 1024, "ｱ" * 1025, "9" * 1023 + "a"]
+    _check_sentences(gpu_tok, oracle_tok, sents)
+
+
+def test_invalid_utf8_rejected(gpu_tok):
+    import kanpyo_b200
+    for bad in [b"\xff", b"\xe3\x81", b"a\x80b", b"\xc0\xaf", b"\xed\xa0\x80", b"\xf4\x90\x80\x80", b"\xe3\x81\x82\xe3"]:
+        with pytest.raises(kanpyo_b200.KanpyoB200Error) as e:
+            gpu_tok.tokenize_batch_bytes(bad, np.array([0, len(bad)], np.uint64))
+        assert e.value.status == -4
+    # a multi-byte char split by a sentence boundary is invalid in both halves
+    b = "あ".encode("utf-8")
+    with pytest.raises(kanpyo_b200.KanpyoB200Error):
+        gpu_tok.tokenize_batch_bytes(b, np.array([0, 1, 3], np.uint64))
+
+
+def test_device_resident_batch(gpu_tok, oracle_tok, vocab):
+    """kp_tokenize_batch_device: text/offsets in HBM, result left in HBM."""
+    import torch
+    from kanpyo_b200 import corpus
+    text, off = corpus.synth_corpus(vocab, 2000, "cfg2")
+    d_text = torch.from_numpy(text.copy()).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    torch.cuda.synchronize()
+    r = gpu_tok.tokenize_batch_device(d_text.data_ptr(), d_off.data_ptr(), len(off) - 1, 0, int(text.size))
+    got = gpu_tok.copy_device_result(r)
+    o_off, o_tok, o_cost, _ = oracle_tok.tokenize_batch(text, off, threads=8)
+    assert_batch_equal(got, o_off, o_tok, o_cost)
+
+
+def test_idempotent_and_sharding_invariant(gpu_tok, vocab):
+    """Size-independent properties at a larger size: same answer twice; same answer when the batch is split."""
+    from kanpyo_b200 import corpus
+    text, off = corpus.synth_corpus(vocab, 20000, "cfg2", seed=7)
+    a = gpu_tok.tokenize_batch_bytes(text, off)
+    b = gpu_tok.tokenize_batch_bytes(text, off)
+    assert np.array_equal(a.tokens, b.tokens) and np.array_equal(a.eos_cost, b.eos_cost)
+    parts = corpus.shard_by_bytes(off, 3)
+    toks, costs = [], []
+    for s0, s1 in parts:
+        sub = gpu_tok.tokenize_batch_bytes(text[int(off[s0]):int(off[s1])], off[s0:s1 + 1] - off[s0])
+        toks.append(sub.tokens)
+        costs.append(sub.eos_cost)
+    assert np.array_equal(np.concatenate(toks), a.tokens) and np.array_equal(np.concatenate(costs), a.eos_cost)
+    # every sentence's tokens tile its bytes exactly and end with EOS
+    t = a.tokens
+    last = a.tok_off[1:].astype(np.int64) - 1
+    assert (t["cls"][last] == 0).all()
+    assert np.array_equal(t["position"][last].astype(np.uint64), np.diff(off))

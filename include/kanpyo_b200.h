@@ -194,6 +194,14 @@ int kp_lattice_dump(kp_tokenizer* t, const uint8_t* utf8, uint64_t len, kp_latti
 int kp_da_common_prefix(kp_tokenizer* t, const uint8_t* utf8, uint64_t len, int expand_dup, int64_t* ids,
                         uint64_t* byte_lens, uint64_t cap, uint64_t* n);
 
+/* ---- dictionary construction support (host only) ------------------------------------------------ */
+/* da::build_with_ids (kanpyo-dict/src/trie/da.rs:206-217): double array over n_keys sorted unique keys
+ * blob[off[k] .. off[k+1]) with leaf ids[k]; produces the same base/check array as the reference.
+ * *out = malloc'ed int32[2 * *out_len] ({base, check} per node); release with kp_da_free. */
+int kp_da_build(const uint8_t* blob, const uint64_t* off, uint64_t n_keys, const int64_t* ids, int32_t** out,
+                uint64_t* out_len);
+void kp_da_free(int32_t* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,8 @@ SYMBOLS = {
     "kp_tokenizer_sync": (C.c_int, [_P]),
     "kp_copy_to_host": (C.c_int, [_P, _P, _P, C.c_uint64]),
     "kp_lattice_dump": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(Lattice)]),
+    "kp_da_build": (C.c_int, [_P, _P, C.c_uint64, _P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
+    "kp_da_free": (None, [_P]),
     "kp_da_common_prefix": (C.c_int, [_P, _P, C.c_uint64, C.c_int, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
 }
 

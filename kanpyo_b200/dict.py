@@ -81,6 +81,15 @@ class Dict:
             self._handle, self._device = h, device
         return self._handle
 
+    def attach_device_blob(self, device_ptr: int, size: int, device: int):
+        """Stage from a packed blob already in HBM on `device` (e.g. the receive buffer of the NCCL
+        broadcast from rank 0) instead of from the host arrays (kp_dict_create_from_device_blob)."""
+        self.close()
+        h = C.c_void_p()
+        _lib.check(_lib.load().kp_dict_create_from_device_blob(device_ptr, size, device, C.byref(h)))
+        self._handle, self._device = h, device
+        return h
+
     def close(self):
         if self._handle is not None:
             _lib.load().kp_dict_destroy(self._handle)

@@ -1,0 +1,263 @@
+"""CPU-only tests of the host side: the C-ABI library loads and exports what include/kanpyo_b200.h
+declares, the product's dictionary builder reproduces the oracle's arrays, the packed blob, and the
+multi-GPU host logic (sharding + gather) under gloo with world_size 2.  No compute call is made here
+(the compute entry points have no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import reference_fixture_dict, to_product_dict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "kanpyo_b200.h"), encoding="utf-8").read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(kp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from kanpyo_b200 import _lib
+    L = _lib.load()
+    names = _header_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), "libkanpyo_b200.so does not export %s" % n
+        assert n in _lib.SYMBOLS, "ctypes binding misses %s" % n
+    assert sorted(_lib.SYMBOLS) == names, "binding declares symbols the header does not"
+    assert L.kp_abi_version() == 1
+    assert L.kp_strerror(-2).decode().startswith("CUDA error or no usable device")
+
+
+def test_library_does_not_depend_on_torch_or_oracle():
+    from kanpyo_b200 import _lib
+    out = subprocess.run(["ldd", _lib.lib_path()], capture_output=True, text=True).stdout
+    assert "torch" not in out and "oracle" not in out and "libcudart" not in out, out
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "kanpyo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "oracle/" not in src and "libkanpyo_oracle" not in src, f
+
+
+def test_compute_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import kanpyo_b200
+    from oracle import oracle
+    d = to_product_dict(reference_fixture_dict(oracle))
+    with pytest.raises(kanpyo_b200.KanpyoB200Error) as e:
+        kanpyo_b200.Tokenizer(d, device=0)
+    assert e.value.status == -2      # KP_ERR_CUDA: no fallback
+
+
+def test_da_build_matches_oracle(oracle_mod):
+    from kanpyo_b200 import builder
+    rng = np.random.default_rng(7)
+    keysets = [[b"a", b"ab", b"abc"], [], [b"\xe3\x81\x82"], [b"hello", b"help", b"world", b"wor"]]
+    alphabet = [bytes([c]) for c in range(1, 256)]
+    keysets.append(sorted({b"".join(rng.choice(alphabet, rng.integers(1, 9))) for _ in range(3000)}))
+    for keys in keysets:
+        keys = sorted(keys)
+        ids = list(range(1, len(keys) + 1))
+        a = builder.da_build(keys, ids)
+        b = oracle_mod.da_build(keys, ids)
+        assert np.array_equal(a, b)
+
+
+def test_da_build_reference_vectors():
+    """da.rs:253-286 / 326-351: every key is found with id i+1 by walking the product-built array."""
+    from kanpyo_b200 import builder
+    for kws in (["a", "ab", "abc", "abcd", "abcde", "abcdef", "abcdefg", "abcdefgh", "abcdefghi", "abcdefghij"],
+                sorted(["こんにちは", "世界", "すもも", "もも", "電気通信大学", "東京都"], key=lambda s: s.encode())):
+        keys = [k.encode("utf-8") for k in kws]
+        da = builder.da_build(keys, list(range(1, len(keys) + 1)))
+
+        def search(key):       # DoubleArray::search, da.rs:133-153
+            p = 1
+            for c in key + b"\x00":
+                q = int(da[p, 0]) + c
+                if not (0 <= q < len(da)) or da[q, 1] != p:
+                    return None
+                p = q
+            return -int(da[p, 0])
+
+        for i, k in enumerate(keys):
+            assert search(k) == i + 1
+        assert search(b"zzz") is None and search(b"") is None
+
+
+def test_builder_matches_oracle_on_ipadic(oracle_ipadic):
+    """The product's DictionaryBuilder and the oracle's restatement of builder.rs are written
+    independently (different EUC-JP handling, parsers and index construction): equal arrays."""
+    from kanpyo_b200 import builder
+    d = builder.ipadic()
+    o = oracle_ipadic
+    for k in ("da", "dup_ids", "dup_counts", "morphs", "conn", "char_category", "invoke_list", "group_list", "unk_cat",
+              "unk_first_id", "unk_count", "unk_morphs"):
+        assert np.array_equal(getattr(d, k), getattr(o, k)), k
+    assert (d.conn_row, d.conn_col) == (o.conn_row, o.conn_col) == (1316, 1316)
+    assert d.keywords == o.keywords and d.char_class == o.char_class
+    assert len(d.keywords) == 392126 and len(set(d.keywords)) == 325871
+
+
+def test_builder_small_directory(tmp_path, oracle_mod):
+    """UTF-8 source tree with a quoted field, duplicates and a char.def override."""
+    from kanpyo_b200 import builder
+    (tmp_path / "a.csv").write_text('辞書,1,1,100,名詞\nテスト,0,0,50,"名,詞"\n辞書,1,1,90,動詞\n', encoding="utf-8")
+    (tmp_path / "b.csv").write_text("あ,2,2,10,感動詞\n", encoding="utf-8")
+    (tmp_path / "matrix.def").write_text("3 3\n0 0 1\n0 1 2\n1 0 3\n2 2 -7\n", encoding="utf-8")
+    (tmp_path / "char.def").write_text("DEFAULT 0 1 0\nKANJI 0 0 2\nHIRAGANA 1 1 0 # c\n\n0x3041..0x309F HIRAGANA\n"
+                                       "0x4E00..0x9FA5 KANJI\n0x3042 KANJI HIRAGANA\n", encoding="utf-8")
+    (tmp_path / "unk.def").write_text("KANJI,1,1,500,名詞\nDEFAULT,0,0,700,記号\nKANJI,1,1,400,名詞\n", encoding="utf-8")
+    d = builder.DictionaryBuilder(str(tmp_path), "utf8").build()
+    assert d.keywords == sorted(k.encode() for k in ["辞書", "テスト", "辞書", "あ"])
+    kws = [k.decode() for k in d.keywords]
+    assert d.morphs[kws.index("テスト")].tolist() == [0, 0, 50]
+    i = kws.index("辞書")
+    assert d.morphs[i].tolist() == [1, 1, 90] and d.morphs[i + 1].tolist() == [1, 1, 100]   # cost orders duplicates
+    assert d.dup_ids.tolist() == [i + 1] and d.dup_counts.tolist() == [1]
+    assert d.features[1][d.features[0][kws.index("テスト")][0]] == "名,詞"
+    conn = d.conn.reshape(3, 3)          # data[c*row + r]
+    assert conn[0, 0] == 1 and conn[1, 0] == 2 and conn[0, 1] == 3 and conn[2, 2] == -7
+    assert d.char_class == ["DEFAULT", "KANJI", "HIRAGANA"]
+    assert d.char_category[0x3042] == 1 and d.char_category[0x3041] == 2 and d.char_category[0x4E00] == 1
+    assert d.invoke_list.tolist() == [0, 0, 1] and d.group_list.tolist() == [1, 0, 1]
+    # unk: sorted by class NAME -> DEFAULT(700) id1, KANJI(400) id2, KANJI(500) id3
+    assert d.unk_cat.tolist() == [0, 1] and d.unk_first_id.tolist() == [1, 2] and d.unk_count.tolist() == [1, 2]
+    assert d.unk_morphs.tolist() == [[0, 0, 700], [1, 1, 400], [1, 1, 500]]
+    od = oracle_mod.dictbuild.from_dir(str(tmp_path), "utf8", oracle_mod.da_build)
+    assert np.array_equal(d.da, od.da) and np.array_equal(d.char_category, od.char_category)
+
+
+def test_builder_errors(tmp_path):
+    from kanpyo_b200 import builder
+    (tmp_path / "a.csv").write_text("あ,0,0,40000,x\n", encoding="utf-8")
+    (tmp_path / "matrix.def").write_text("1 1\n0 0 0\n")
+    (tmp_path / "char.def").write_text("DEFAULT 0 0 0\n")
+    (tmp_path / "unk.def").write_text("DEFAULT,0,0,0,x\n")
+    with pytest.raises(builder.BuilderError):      # builder.rs:59-61
+        builder.DictionaryBuilder(str(tmp_path), "utf8").build()
+    (tmp_path / "a.csv").write_text("あ,0,0,4,x\n", encoding="utf-8")
+    (tmp_path / "char.def").write_text("DEFAULT 0 0 0\n0x00e0 DEFAULT\n")      # lower-case hex: no regex matches
+    with pytest.raises(builder.BuilderError):
+        builder.DictionaryBuilder(str(tmp_path), "utf8").build()
+    (tmp_path / "char.def").write_text("DEFAULT 0 0 0\n")
+    (tmp_path / "matrix.def").write_text("1 1\n0 0 99999\n")                  # matrix_def.rs:54
+    with pytest.raises(builder.BuilderError):
+        builder.DictionaryBuilder(str(tmp_path), "utf8").build()
+
+
+def test_dict_pack_blob_is_validated(oracle_mod):
+    from kanpyo_b200 import _lib
+    d = to_product_dict(reference_fixture_dict(oracle_mod))
+    blob = d.pack()
+    assert blob[:8].tobytes() == b"PKB200D1" and blob.size % 256 == 0
+    L = _lib.load()
+    bad = to_product_dict(reference_fixture_dict(oracle_mod))
+    bad.morphs = bad.morphs.copy()
+    bad.morphs[0, 0] = 7                   # left_id outside the 3x3 matrix: the reference would panic
+    a, _keep = bad._arrays()
+    size = C.c_uint64()
+    assert L.kp_dict_pack(C.byref(a), None, 0, C.byref(size)) == _lib.KP_ERR_DICT
+    assert b"" != L.kp_last_error()
+
+
+def test_shard_by_bytes_balances_and_covers():
+    from kanpyo_b200.corpus import shard_by_bytes
+    rng = np.random.default_rng(3)
+    lens = rng.integers(0, 500, 1000)
+    lens[10] = 40000
+    off = np.zeros(1001, np.uint64)
+    off[1:] = np.cumsum(lens)
+    for n in (1, 2, 3, 8):
+        sh = shard_by_bytes(off, n)
+        assert sh[0][0] == 0 and sh[-1][1] == 1000
+        assert all(sh[i][1] == sh[i + 1][0] for i in range(n - 1))
+        sizes = [int(off[b] - off[a]) for a, b in sh]
+        assert max(sizes) - min(sizes) <= 40000 + 500
+    assert shard_by_bytes(np.zeros(1, np.uint64), 4) == [(0, 0)] * 4
+
+
+_WORKER = r"""
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+from kanpyo_b200 import sharded, corpus
+from kanpyo_b200.tokenizer import TOKEN_DTYPE
+from oracle import oracle
+from helpers import reference_fixture_dict, to_product_dict
+
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+od = reference_fixture_dict(oracle)
+# 1. dictionary blob broadcast: only rank 0 packs
+blob = to_product_dict(od).pack() if rank == 0 else None
+t = sharded.broadcast_dict_blob(blob, 0, "cpu")
+expect = to_product_dict(od).pack()
+assert np.array_equal(t.numpy(), expect), "blob differs after broadcast"
+# 2. shard, tokenize locally (CPU oracle stands in for the device pass), gather on rank 0
+sents = ["テスト", "", "辞書テスト形態素", "あいうえお", "漢字", "テストテストテスト" * 5, "x", "形態素"] * 3
+blobs = [s.encode() for s in sents]
+off = np.zeros(len(blobs) + 1, np.uint64); off[1:] = np.cumsum([len(b) for b in blobs])
+text = np.frombuffer(b"".join(blobs), np.uint8)
+otk = oracle.OracleTokenizer(od)
+s0, s1 = corpus.shard_by_bytes(off, world)[rank]
+l_off, l_tok, l_cost, _ = otk.tokenize_batch(text, off[s0:s1 + 1])
+rec = np.zeros(len(l_tok), TOKEN_DTYPE)
+rec["id"], rec["cls"], rec["position"], rec["start"] = l_tok[:, 0], l_tok[:, 1], l_tok[:, 2], l_tok[:, 3]
+rec["char_len"] = l_tok[:, 4] - l_tok[:, 3]
+g = sharded.gather_results(torch.from_numpy(l_off.view(np.int64).copy()), torch.from_numpy(rec.view(np.uint8).copy()),
+                           torch.from_numpy(l_cost.copy()))
+if rank == 0:
+    res = sharded.to_batch_result(*g)
+    f_off, f_tok, f_cost, _ = otk.tokenize_batch(text, off)
+    assert np.array_equal(res.tok_off, f_off), (res.tok_off, f_off)
+    assert np.array_equal(res.eos_cost, f_cost)
+    assert np.array_equal(res.tokens["id"].astype(np.int64), f_tok[:, 0])
+    assert np.array_equal(res.tokens["position"].astype(np.int64), f_tok[:, 2])
+    assert np.array_equal(res.tokens["start"].astype(np.int64) + res.tokens["char_len"], f_tok[:, 4])
+else:
+    assert g is None
+# 3. an empty shard still takes part
+e = sharded.gather_results(torch.zeros(1, dtype=torch.int64), torch.zeros(0, dtype=torch.uint8),
+                           torch.zeros(0, dtype=torch.int32))
+if rank == 0:
+    assert e[0].tolist() == [0] and e[1].numel() == 0
+dist.barrier()
+dist.destroy_process_group()
+print("worker", rank, "ok")
+"""
+
+
+def test_sharded_gather_gloo_world2(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   GLOO_SOCKET_IFNAME="lo")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, "rank %d failed:\n%s" % (r, o)
+        assert "worker %d ok" % r in o

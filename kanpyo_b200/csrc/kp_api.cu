@@ -85,7 +85,7 @@ struct kp_tokenizer {
     uint64_t chunk_bytes = 64ull << 20;
     bool count_work = false;
     // chunk scratch
-    DevBuf text, off, nchar, coff, binfo, ncount, noff, bcount, boff, bfill, rec, slot, bright, bnode, bdp, pre,
+    DevBuf text, off, nchar, coff, binfo, ncount, noff, bcount, boff, bfill, rec, tgt, bent, bnode, path, pre,
         tcount, toff32, scan_tmp, totals, err;
     // device outputs
     DevBuf d_tok_off, d_tokens, d_eos;
@@ -185,19 +185,17 @@ int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_token
     }
     const size_t N = c.N;
     KP_TRY(t->rec.ensure(sizeof(uint4) * (N + 1)));
-    KP_TRY(t->slot.ensure(sizeof(uint32_t) * (N + 1)));
-    KP_TRY(t->bright.ensure(sizeof(int16_t) * (N + 2)));
+    KP_TRY(t->tgt.ensure(sizeof(uint2) * (N + 1)));
+    KP_TRY(t->bent.ensure(sizeof(int2) * (N + 1)));
     KP_TRY(t->bnode.ensure(sizeof(uint32_t) * (N + 1)));
-    KP_TRY(t->bdp.ensure(sizeof(int32_t) * (N + 1)));
-    KP_TRY(t->pre.ensure(sizeof(uint32_t) * (N + 1)));
+    KP_TRY(t->path.ensure(sizeof(uint32_t) * (NB + 1)));
     KP_TRY(t->tcount.ensure(sizeof(uint32_t) * (S + 1)));
     KP_TRY(t->toff32.ensure(sizeof(uint32_t) * (S + 2)));
     c.rec = t->rec.as<uint4>();
-    c.slot = t->slot.as<uint32_t>();
-    c.bright = t->bright.as<int16_t>();
+    c.tgt = t->tgt.as<uint2>();
+    c.bent = t->bent.as<int2>();
     c.bnode = t->bnode.as<uint32_t>();
-    c.bdp = t->bdp.as<int32_t>();
-    c.pre = t->pre.as<uint32_t>();
+    c.path = t->path.as<uint32_t>();
     c.tcount = t->tcount.as<uint32_t>();
     c.toff32 = t->toff32.as<uint32_t>();
 
@@ -209,7 +207,7 @@ int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_token
     KP_LAUNCH(kp_launch_viterbi(c, d, st));
     if (t->count_work) KP_LAUNCH(kp_launch_pair_count(c, st));
     KP_CUDA(cudaEventRecord(t->ev[EV_VITERBI], st));
-    KP_LAUNCH(kp_launch_backtrace_count(c, st));
+    KP_LAUNCH(kp_launch_backtrace_count(c, d, st));
     KP_LAUNCH(kp_launch_scan(c.tcount, c.toff32, S, c.scan_tmp, &c.totals[3], st));
     KP_LAUNCH(kp_launch_backtrace_write(c, tok_base, st));
     KP_CUDA(cudaEventRecord(t->ev[EV_BACKTRACE], st));
@@ -274,7 +272,7 @@ extern "C" void kp_tokenizer_destroy(kp_tokenizer* t) {
     cudaSetDevice(t->device);
     if (t->stream) cudaStreamSynchronize(t->stream);
     DevBuf* bufs[] = {&t->text, &t->off, &t->nchar, &t->coff, &t->binfo, &t->ncount, &t->noff, &t->bcount, &t->boff,
-                      &t->bfill, &t->rec, &t->slot, &t->bright, &t->bnode, &t->bdp, &t->pre, &t->tcount, &t->toff32,
+                      &t->bfill, &t->rec, &t->tgt, &t->bent, &t->bnode, &t->path, &t->pre, &t->tcount, &t->toff32,
                       &t->scan_tmp, &t->totals, &t->err, &t->d_tok_off, &t->d_tokens, &t->d_eos};
     for (DevBuf* b : bufs) b->release();
     PinBuf* pins[] = {&t->h_totals, &t->h_tok_off, &t->h_tokens, &t->h_eos, &t->h_misc};
@@ -450,15 +448,31 @@ extern "C" int kp_lattice_dump(kp_tokenizer* t, const uint8_t* utf8, uint64_t le
     // scratch of the (single-chunk) pass is still intact
     const uint32_t N = (uint32_t)(t->counters.nodes - 1);   // device nodes (no BOS)
     const uint32_t NB = (uint32_t)t->counters.chars + 1;
+    // pre_nodes for every node: recomputed on the device from the dp table (the sweep keeps dp only)
+    {
+        KP_TRY(t->pre.ensure(sizeof(uint32_t) * ((size_t)N + 1)));
+        kp_chunk c;
+        memset(&c, 0, sizeof(c));
+        c.N = N;
+        c.rec = t->rec.as<uint4>();
+        c.tgt = t->tgt.as<uint2>();
+        c.bent = t->bent.as<int2>();
+        c.boff = t->boff.as<uint32_t>();
+        c.eos_cost = t->d_eos.as<int32_t>();
+        c.pre = t->pre.as<uint32_t>();
+        KP_TRY(kp_launch_fill_pre(c, t->dict->view, t->stream));
+        KP_CUDA(cudaStreamSynchronize(t->stream));
+    }
     std::vector<uint4> rec(N), binfo(NB);
-    std::vector<uint32_t> slot(N), bnode(N), pre(N);
-    std::vector<int32_t> bdp(N);
+    std::vector<uint32_t> bnode(N), pre(N);
+    std::vector<uint2> tgt(N);
+    std::vector<int2> bent(N);
     KP_CUDA(cudaMemcpy(rec.data(), t->rec.p, sizeof(uint4) * N, cudaMemcpyDeviceToHost));
     KP_CUDA(cudaMemcpy(binfo.data(), t->binfo.p, sizeof(uint4) * NB, cudaMemcpyDeviceToHost));
-    KP_CUDA(cudaMemcpy(slot.data(), t->slot.p, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost));
+    KP_CUDA(cudaMemcpy(tgt.data(), t->tgt.p, sizeof(uint2) * N, cudaMemcpyDeviceToHost));
     KP_CUDA(cudaMemcpy(bnode.data(), t->bnode.p, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost));
     KP_CUDA(cudaMemcpy(pre.data(), t->pre.p, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost));
-    KP_CUDA(cudaMemcpy(bdp.data(), t->bdp.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost));
+    KP_CUDA(cudaMemcpy(bent.data(), t->bent.p, sizeof(int2) * N, cudaMemcpyDeviceToHost));
     t->lattice_nodes.assign((size_t)N + 1, kp_lattice_node{});
     kp_lattice_node& bos = t->lattice_nodes[0];
     bos.id = 0;
@@ -477,7 +491,7 @@ extern "C" int kp_lattice_dump(kp_tokenizer* t, const uint8_t* utf8, uint64_t le
         o.left_id = (int16_t)(x.z & 0xFFFF);
         o.right_id = (int16_t)(x.z >> 16);
         o.cost = (int16_t)(x.w & 0xFFFF);
-        o.dp = kind == KP_CLASS_DUMMY ? r.eos_cost[0] : bdp[slot[i]];
+        o.dp = kind == KP_CLASS_DUMMY ? r.eos_cost[0] : bent[tgt[i].y].x;
         o.pre = pre[i] == KP_NONE ? -1 : (bnode[pre[i]] == KP_NONE ? 0 : (int32_t)bnode[pre[i]] + 1);
     }
     out->n_nodes = (uint64_t)N + 1;
@@ -493,18 +507,18 @@ extern "C" int kp_da_common_prefix(kp_tokenizer* t, const uint8_t* utf8, uint64_
     const uint32_t dcap = (uint32_t)std::min<uint64_t>(cap, 1u << 20);
     KP_TRY(t->text.ensure(len + 16));
     KP_TRY(t->rec.ensure(sizeof(int64_t) * (dcap + 1)));
-    KP_TRY(t->bdp.ensure(sizeof(uint64_t) * (dcap + 1)));
+    KP_TRY(t->bent.ensure(sizeof(uint64_t) * (dcap + 1)));
     KP_TRY(t->err.ensure(sizeof(uint32_t) * 2));
     if (len) KP_CUDA(cudaMemcpyAsync(t->text.p, utf8, len, cudaMemcpyHostToDevice, st));
     KP_TRY(kp_launch_common_prefix(t->dict->view, t->text.as<uint8_t>(), (uint32_t)len, expand_dup, t->rec.as<int64_t>(),
-                                   t->bdp.as<uint64_t>(), dcap, t->err.as<uint32_t>(), st));
+                                   t->bent.as<uint64_t>(), dcap, t->err.as<uint32_t>(), st));
     uint32_t hn = 0;
     KP_CUDA(cudaMemcpyAsync(&hn, t->err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaStreamSynchronize(st));
     const uint32_t m = std::min(hn, dcap);
     if (m) {
         KP_CUDA(cudaMemcpy(ids, t->rec.p, sizeof(int64_t) * m, cudaMemcpyDeviceToHost));
-        KP_CUDA(cudaMemcpy(byte_lens, t->bdp.p, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost));
+        KP_CUDA(cudaMemcpy(byte_lens, t->bent.p, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost));
     }
     *n = hn;
     return KP_OK;

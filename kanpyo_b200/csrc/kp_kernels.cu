@@ -453,7 +453,8 @@ int kp_launch_lattice_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st
 
 // =================================================================================================
 // Bucketize: stable placement of every node into its end bucket (the reference's edges[end] lists,
-// ascending node index).  One warp per sentence walks its nodes in order, 32 at a time.
+// ascending node index).  One warp per sentence walks its nodes in order, 32 at a time, and writes
+// the two packed views the Viterbi sweep reads: tgt[node] and bent[bucket slot].
 // =================================================================================================
 constexpr int SENT_THREADS = 128;   // 4 sentences per CTA
 
@@ -461,8 +462,8 @@ __global__ void __launch_bounds__(SENT_THREADS) kp_bucketize(uint32_t S, const u
                                                              const uint32_t* __restrict__ noff,
                                                              const uint32_t* __restrict__ boff,
                                                              const uint4* __restrict__ rec, uint32_t* __restrict__ bfill,
-                                                             uint32_t* __restrict__ slot, int16_t* __restrict__ bright,
-                                                             uint32_t* __restrict__ bnode, int32_t* __restrict__ bdp) {
+                                                             uint2* __restrict__ tgt, int2* __restrict__ bent,
+                                                             uint32_t* __restrict__ bnode) {
     uint32_t s = (blockIdx.x * SENT_THREADS + threadIdx.x) >> 5;
     if (s >= S) return;
     const uint32_t lane = lane_id();
@@ -470,9 +471,9 @@ __global__ void __launch_bounds__(SENT_THREADS) kp_bucketize(uint32_t S, const u
     const uint32_t n0 = noff[bb], n1 = noff[bb + n];   // nodes before the EOS node (which is node n1)
     if (lane == 0) {
         uint32_t q = boff[bb];                          // BOS: dp None -> unwrap_or(0) (lattice.rs:127)
-        bright[q] = 0;
+        bent[q] = make_int2(0, 0);
         bnode[q] = KP_NONE;
-        bdp[q] = 0;
+        tgt[n1] = make_uint2(0u, KP_NONE);              // EOS: morph (0,0,0), no bucket entry needed
     }
     for (uint32_t i0 = n0; i0 < n1; i0 += 32) {
         uint32_t i = i0 + lane;
@@ -489,8 +490,8 @@ __global__ void __launch_bounds__(SENT_THREADS) kp_bucketize(uint32_t S, const u
         old = __shfl_sync(KP_FULL, old, leader);
         if (valid) {
             uint32_t q = boff[e] + old + (uint32_t)__popc(m & lanemask_lt()) + (e == bb ? 1u : 0u);
-            slot[i] = q;
-            bright[q] = (int16_t)(r.z >> 16);
+            tgt[i] = make_uint2((r.z & 0xFFFFu) | (r.w << 16), q);
+            bent[q] = make_int2(KP_INF, (int)((r.z >> 16) * 2u));   // right_id as a byte offset into a conn row
             bnode[q] = i;
         }
         __syncwarp();
@@ -500,72 +501,83 @@ __global__ void __launch_bounds__(SENT_THREADS) kp_bucketize(uint32_t S, const u
 int kp_launch_bucketize(const kp_chunk& c, cudaStream_t st) {
     if (c.S == 0) return 0;
     uint32_t blocks = (uint32_t)(((uint64_t)c.S * 32 + SENT_THREADS - 1) / SENT_THREADS);
-    kp_bucketize<<<blocks, SENT_THREADS, 0, st>>>(c.S, c.coff, c.noff, c.boff, c.rec, c.bfill, c.slot, c.bright, c.bnode,
-                                                  c.bdp);
+    kp_bucketize<<<blocks, SENT_THREADS, 0, st>>>(c.S, c.coff, c.noff, c.boff, c.rec, c.bfill, c.tgt, c.bent, c.bnode);
     return kp_launch_check("kp_bucketize");
 }
 
 // =================================================================================================
-// Viterbi forward sweep: one warp per sentence, boundary by boundary.  Lanes hold the nodes ENDING
-// at the boundary (dp, right_id); for every node STARTING there the lanes gather
-// conn[left*row + right] and a warp min-reduction picks the first minimal predecessor.
-//   total = min(dp[j] + cost_i + conn(right_j, left_i), INF); strict '<' from INF  (lattice.rs:121-141)
+// Viterbi forward sweep (lattice.rs:116-143, dp values only).
+//
+// A warp carries 4 sentences, 8 lanes each, and steps all of them boundary by boundary with
+// warp-uniform loop bounds, so the four groups share every issued instruction.  Lanes hold the nodes
+// STARTING at the boundary (targets); each lane folds the nodes ENDING there (predecessors) with one
+// DPX add-min per pair:   best = min(best, dp[j] + conn(right_j, left_i))          connection.rs:12-14
+//   dp[i] = min(best + cost_i, INF), kept only if < INF                            lattice.rs:127-139
+// Out-of-range predecessor slots are clamped to the bucket's last entry: a duplicate never changes a
+// minimum.  The argmin (pre_nodes) is NOT tracked here: the back-trace recomputes it for the ~30
+// nodes per sentence that lie on the best path (first j attaining dp[i], which is what the strict '<'
+// update of lattice.rs:136 selects).  dp travels from a target to its end bucket through
+// bent[slot].x; the __syncwarp orders that store before the next boundary's loads.
 // =================================================================================================
-__global__ void __launch_bounds__(SENT_THREADS) kp_viterbi(uint32_t S, const uint32_t* __restrict__ coff,
-                                                           const uint32_t* __restrict__ noff,
-                                                           const uint32_t* __restrict__ boff,
-                                                           const uint4* __restrict__ rec,
-                                                           const uint32_t* __restrict__ slot,
-                                                           const int16_t* __restrict__ bright, int32_t* bdp,
-                                                           uint32_t* __restrict__ pre, int32_t* __restrict__ eos_cost,
-                                                           const int16_t* __restrict__ conn, uint32_t conn_row) {
-    uint32_t s = (blockIdx.x * SENT_THREADS + threadIdx.x) >> 5;
-    if (s >= S) return;
-    const uint32_t lane = lane_id();
-    const uint32_t bb = coff[s] + s, n = coff[s + 1] - coff[s];
-    uint32_t t0 = noff[bb], q0 = boff[bb];
-    for (uint32_t p = 0; p <= n; p++) {
-        const uint32_t b = bb + p;
-        const uint32_t t1 = noff[b + 1], q1 = boff[b + 1];
-        const uint32_t np = q1 - q0;
-        for (uint32_t tc = t0; tc < t1; tc += 32) {
-            const uint32_t i = tc + lane;
-            const bool tvalid = i < t1;
-            uint4 r = tvalid ? rec[i] : make_uint4(0, 0, 0, 0);
-            const uint32_t left_off = (r.z & 0xFFFFu) * conn_row;
-            const int cost = (int)(int16_t)(r.w & 0xFFFFu);
+constexpr int VIT_GROUP = 8;
+constexpr int VIT_THREADS = 128;
+
+__device__ __forceinline__ int ld_conn(const char* p) {
+    int v;
+    asm("ld.global.nc.s16 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(VIT_THREADS) kp_viterbi(uint32_t S, const uint32_t* __restrict__ coff,
+                                                          const uint32_t* __restrict__ noff,
+                                                          const uint32_t* __restrict__ boff,
+                                                          const uint2* __restrict__ tgt, int2* bent,
+                                                          int32_t* __restrict__ eos_cost,
+                                                          const int16_t* __restrict__ conn, uint32_t conn_row) {
+    const uint32_t s = (blockIdx.x * VIT_THREADS + threadIdx.x) / VIT_GROUP;
+    const uint32_t l = threadIdx.x & (VIT_GROUP - 1);
+    const bool has = s < S;
+    uint32_t bb = 0, n = 0;
+    if (has) {
+        bb = coff[s] + s;
+        n = coff[s + 1] - coff[s];
+    }
+    const uint32_t steps = __reduce_max_sync(KP_FULL, has ? n + 1 : 0u);
+    uint32_t t0 = 0, q0 = 0, t1n = 0, q1n = 0;
+    if (has) {
+        t0 = noff[bb];
+        q0 = boff[bb];
+        t1n = noff[bb + 1];
+        q1n = boff[bb + 1];
+    }
+    const size_t row_bytes = (size_t)conn_row * 2;
+    for (uint32_t p = 0; p < steps; p++) {
+        const bool act = has && p <= n;
+        const uint32_t t1 = act ? t1n : t0, q1 = act ? q1n : q0;
+        if (has && p < n) {                       // bounds of the next boundary, off the critical path
+            t1n = noff[bb + p + 2];
+            q1n = boff[bb + p + 2];
+        }
+        const uint32_t T = t1 - t0, P = q1 - q0;
+        const uint32_t Tmax = __reduce_max_sync(KP_FULL, T), Pmax = __reduce_max_sync(KP_FULL, P);
+        const uint32_t qb = P ? q0 : 0u, qlast = P ? q1 - 1 : 0u;    // P == 0: harmless reads of entry 0
+        for (uint32_t tc = 0; tc < Tmax; tc += VIT_GROUP) {
+            const bool tv = tc + l < T;
+            const uint2 tg = tv ? tgt[t0 + tc + l] : make_uint2(0u, KP_NONE);
+            const char* crow = (const char*)conn + (size_t)(tg.x & 0xFFFFu) * row_bytes;
             int best = INT_MAX;
-            uint32_t arg = KP_NONE;
-            const uint32_t ntc = min(32u, t1 - tc);
-            for (uint32_t pc = q0; pc < q1; pc += 32) {
-                const uint32_t j = pc + lane;
-                const bool pvalid = j < q1;
-                const int dpj = pvalid ? bdp[j] : 0;
-                const uint32_t rj = pvalid ? (uint32_t)(uint16_t)bright[j] : 0u;
-                for (uint32_t t = 0; t < ntc; t++) {
-                    uint32_t lo = __shfl_sync(KP_FULL, left_off, t);
-                    int v = pvalid ? dpj + (int)conn[lo + rj] : INT_MAX;     // connection.rs:12-14
-                    int m = __reduce_min_sync(KP_FULL, v);
-                    uint32_t first = (uint32_t)__ffs(__ballot_sync(KP_FULL, v == m)) - 1;
-                    if (lane == t && m < best) {     // strict: the first minimum wins (lattice.rs:136)
-                        best = m;
-                        arg = pc + first;
-                    }
+            for (uint32_t jj = 0; jj < Pmax; jj += 4) {
+#pragma unroll
+                for (uint32_t u = 0; u < 4; u++) {
+                    const int2 e = bent[min(qb + jj + u, qlast)];
+                    best = __viaddmin_s32(e.x, ld_conn(crow + (uint32_t)e.y), best);
                 }
             }
-            if (tvalid) {
+            if (tv) {
                 int dp = KP_INF;
-                uint32_t pr = KP_NONE;
-                if (np != 0 && best != INT_MAX) {
-                    int total = best + cost;
-                    if (total < KP_INF) {
-                        dp = total;
-                        pr = arg;
-                    }
-                }
-                pre[i] = pr;
-                if ((r.x >> KP_KIND_SHIFT) == KP_CLASS_DUMMY) eos_cost[s] = dp;
-                else bdp[slot[i]] = dp;
+                if (P) dp = min(best + (int)(int16_t)(tg.x >> 16), KP_INF);
+                if (tg.y == KP_NONE) eos_cost[s] = dp;
+                else bent[tg.y].x = dp;
             }
         }
         __syncwarp();
@@ -576,10 +588,44 @@ __global__ void __launch_bounds__(SENT_THREADS) kp_viterbi(uint32_t S, const uin
 
 int kp_launch_viterbi(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
     if (c.S == 0) return 0;
-    uint32_t blocks = (uint32_t)(((uint64_t)c.S * 32 + SENT_THREADS - 1) / SENT_THREADS);
-    kp_viterbi<<<blocks, SENT_THREADS, 0, st>>>(c.S, c.coff, c.noff, c.boff, c.rec, c.slot, c.bright, c.bdp, c.pre,
-                                                c.eos_cost, d.conn, d.conn_row);
+    uint32_t blocks = (uint32_t)(((uint64_t)c.S * VIT_GROUP + VIT_THREADS - 1) / VIT_THREADS);
+    kp_viterbi<<<blocks, VIT_THREADS, 0, st>>>(c.S, c.coff, c.noff, c.boff, c.tgt, c.bent, c.eos_cost, d.conn, d.conn_row);
     return kp_launch_check("kp_viterbi");
+}
+
+// pre_nodes[i] for EVERY node (lattice.rs:136-139), recomputed from the dp values: the first
+// predecessor attaining dp[i].  Only the lattice dump needs it (one thread per node).
+__device__ __forceinline__ uint32_t kp_first_argmin(const int2* __restrict__ bent, uint32_t q0, uint32_t q1,
+                                                    const char* crow, int want) {
+    for (uint32_t j = q0; j < q1; j++) {
+        const int2 e = bent[j];
+        if (e.x + ld_conn(crow + (uint32_t)e.y) == want) return j;
+    }
+    return KP_NONE;
+}
+
+__global__ void __launch_bounds__(256) kp_fill_pre(uint32_t N, const uint4* __restrict__ rec,
+                                                   const uint2* __restrict__ tgt, const int2* __restrict__ bent,
+                                                   const uint32_t* __restrict__ boff,
+                                                   const int32_t* __restrict__ eos_cost, uint32_t* __restrict__ pre,
+                                                   const int16_t* __restrict__ conn, uint32_t conn_row) {
+    uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    const uint2 tg = tgt[i];
+    const uint32_t b = rec[i].y;
+    const int dp = tg.y == KP_NONE ? eos_cost[0] : bent[tg.y].x;     // dump runs on a single sentence
+    uint32_t pr = KP_NONE;
+    if (dp < KP_INF)
+        pr = kp_first_argmin(bent, boff[b], boff[b + 1], (const char*)conn + (size_t)(tg.x & 0xFFFFu) * conn_row * 2,
+                             dp - (int)(int16_t)(tg.x >> 16));
+    pre[i] = pr;
+}
+
+int kp_launch_fill_pre(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
+    if (c.N == 0) return 0;
+    kp_fill_pre<<<(c.N + 255) / 256, 256, 0, st>>>(c.N, c.rec, c.tgt, c.bent, c.boff, c.eos_cost, c.pre, d.conn,
+                                                   d.conn_row);
+    return kp_launch_check("kp_fill_pre");
 }
 
 // E = sum over boundaries of (#targets x #predecessors): the pairs visited by lattice.rs:122-125
@@ -599,57 +645,81 @@ int kp_launch_pair_count(const kp_chunk& c, cudaStream_t st) {
 }
 
 // =================================================================================================
-// Back-trace (lattice.rs:144-153) + Node -> Token (tokenizer.rs:22-43).  One thread per sentence:
-// pass 1 counts the path, pass 2 (after the scan) writes it front to back.
+// Back-trace (lattice.rs:144-153) + Node -> Token (tokenizer.rs:22-43).  One thread per sentence.
+// Pass 1 walks from the EOS node, recomputing each predecessor as the first j with
+// dp[j] + conn + cost == dp[i], and parks the path (node indices, back to front) in `path`;
+// pass 2 (after the scan of the path lengths) writes the tokens front to back.
 // =================================================================================================
-template <bool WRITE>
-__global__ void __launch_bounds__(128) kp_backtrace(uint32_t S, const uint32_t* __restrict__ coff,
-                                                    const uint32_t* __restrict__ noff, const uint4* __restrict__ rec,
-                                                    const uint32_t* __restrict__ pre, const uint32_t* __restrict__ bnode,
-                                                    const uint4* __restrict__ binfo, uint32_t* __restrict__ tcount,
-                                                    const uint32_t* __restrict__ toff, uint64_t tok_base,
-                                                    uint64_t* __restrict__ tok_off, kp_token* __restrict__ tokens) {
+__global__ void __launch_bounds__(128) kp_backtrace_find(uint32_t S, const uint32_t* __restrict__ coff,
+                                                         const uint32_t* __restrict__ noff,
+                                                         const uint32_t* __restrict__ boff,
+                                                         const uint4* __restrict__ rec, const uint2* __restrict__ tgt,
+                                                         const int2* __restrict__ bent,
+                                                         const uint32_t* __restrict__ bnode,
+                                                         const int32_t* __restrict__ eos_cost,
+                                                         const int16_t* __restrict__ conn, uint32_t conn_row,
+                                                         uint32_t* __restrict__ path, uint32_t* __restrict__ tcount) {
     uint32_t s = blockIdx.x * 128 + threadIdx.x;
-    if (s > S) return;
-    if (WRITE) tok_off[s] = tok_base + toff[s];
-    if (s == S) return;
+    if (s >= S) return;
     const uint32_t bb = coff[s] + s, n = coff[s + 1] - coff[s];
     uint32_t cur = noff[bb + n];                 // `self.nodes.len() - 1`: the EOS node
-    const uint32_t sent_byte0 = binfo[bb].x;     // for n == 0 this is the EOS boundary: also the sentence start
     uint32_t cnt = 0;
-    uint32_t w = WRITE ? toff[s + 1] : 0;        // one past this sentence's last token
+    int dp = eos_cost[s];
     while (true) {
-        uint32_t q = pre[cur];
-        if (q == KP_NONE) break;                 // `while let Some(pre) = pre_nodes[pos]`
-        if (WRITE) {
-            uint4 r = rec[cur];
-            uint32_t kind = r.x >> KP_KIND_SHIFT;
-            kp_token t;
-            t.id = (int32_t)(r.x & KP_ID_MASK);
-            t.position = binfo[r.y].x - sent_byte0;
-            t.start = r.y - bb;
-            t.char_len = kind == KP_CLASS_DUMMY ? 3 : (uint16_t)(r.w >> 16);   // "EOS".chars().count()
-            t.cls = (uint8_t)kind;
-            t.reserved = 0;
-            tokens[--w] = t;
-        }
+        if (dp >= KP_INF) break;                 // pre_nodes[pos] is None: no total < INF was ever seen
+        const uint2 tg = tgt[cur];
+        const uint32_t b = rec[cur].y;
+        const uint32_t q = kp_first_argmin(bent, boff[b], boff[b + 1],
+                                           (const char*)conn + (size_t)(tg.x & 0xFFFFu) * conn_row * 2,
+                                           dp - (int)(int16_t)(tg.x >> 16));
+        if (q == KP_NONE) break;                 // unreachable for a consistent dp table
+        path[bb + cnt] = cur;                    // path length <= n + 1 = boundaries of the sentence
         cnt++;
         cur = bnode[q];
         if (cur == KP_NONE) break;               // reached BOS, which has no predecessor and is not emitted
+        dp = bent[q].x;
     }
-    if (!WRITE) tcount[s] = cnt;
+    tcount[s] = cnt;
 }
 
-int kp_launch_backtrace_count(const kp_chunk& c, cudaStream_t st) {
-    kp_backtrace<false><<<(c.S + 1 + 127) / 128, 128, 0, st>>>(c.S, c.coff, c.noff, c.rec, c.pre, c.bnode, c.binfo,
-                                                               c.tcount, nullptr, 0, nullptr, nullptr);
-    return kp_launch_check("kp_backtrace<count>");
+__global__ void __launch_bounds__(128) kp_backtrace_emit(uint32_t S, const uint32_t* __restrict__ coff,
+                                                         const uint4* __restrict__ rec,
+                                                         const uint4* __restrict__ binfo,
+                                                         const uint32_t* __restrict__ path,
+                                                         const uint32_t* __restrict__ toff, uint64_t tok_base,
+                                                         uint64_t* __restrict__ tok_off, kp_token* __restrict__ tokens) {
+    uint32_t s = blockIdx.x * 128 + threadIdx.x;
+    if (s > S) return;
+    tok_off[s] = tok_base + toff[s];
+    if (s == S) return;
+    const uint32_t bb = coff[s] + s;
+    const uint32_t sent_byte0 = binfo[bb].x;     // for n == 0 this is the EOS boundary: also the sentence start
+    const uint32_t w0 = toff[s], cnt = toff[s + 1] - w0;
+    for (uint32_t k = 0; k < cnt; k++) {
+        const uint4 r = rec[path[bb + cnt - 1 - k]];
+        const uint32_t kind = r.x >> KP_KIND_SHIFT;
+        kp_token t;
+        t.id = (int32_t)(r.x & KP_ID_MASK);
+        t.position = binfo[r.y].x - sent_byte0;
+        t.start = r.y - bb;
+        t.char_len = kind == KP_CLASS_DUMMY ? 3 : (uint16_t)(r.w >> 16);   // "EOS".chars().count()
+        t.cls = (uint8_t)kind;
+        t.reserved = 0;
+        tokens[w0 + k] = t;
+    }
+}
+
+int kp_launch_backtrace_count(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
+    if (c.S == 0) return 0;
+    kp_backtrace_find<<<(c.S + 127) / 128, 128, 0, st>>>(c.S, c.coff, c.noff, c.boff, c.rec, c.tgt, c.bent, c.bnode,
+                                                         c.eos_cost, d.conn, d.conn_row, c.path, c.tcount);
+    return kp_launch_check("kp_backtrace_find");
 }
 
 int kp_launch_backtrace_write(const kp_chunk& c, uint64_t tok_base, cudaStream_t st) {
-    kp_backtrace<true><<<(c.S + 1 + 127) / 128, 128, 0, st>>>(c.S, c.coff, c.noff, c.rec, c.pre, c.bnode, c.binfo,
-                                                              nullptr, c.toff32, tok_base, c.tok_off, c.tokens);
-    return kp_launch_check("kp_backtrace<write>");
+    kp_backtrace_emit<<<(c.S + 1 + 127) / 128, 128, 0, st>>>(c.S, c.coff, c.rec, c.binfo, c.path, c.toff32, tok_base,
+                                                             c.tok_off, c.tokens);
+    return kp_launch_check("kp_backtrace_emit");
 }
 
 // =================================================================================================

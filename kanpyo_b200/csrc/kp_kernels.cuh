@@ -9,9 +9,12 @@
 //   ncount/noff u32[NB+1] nodes STARTING at each boundary (count / exclusive scan) = reference insertion order
 //   bcount/boff u32[NB+1] nodes ENDING at each boundary (+BOS at p=0)  = the reference's `edges` buckets
 //   rec     uint4[N]      node {id|class<<30, start boundary, left|right<<16, cost|char_len<<16}
-//   slot    u32[N]        position of the node in its end bucket (global index into the b* arrays)
-//   bright  i16[N], bnode u32[N], bdp i32[N]   per bucket entry: right_id, node index, dp value
-//   pre     u32[N]        predecessor as a bucket slot (KP_NONE = Option::None)
+//   tgt     uint2[N]      per node, what the Viterbi sweep needs of a TARGET: {left | cost<<16, bucket slot}
+//                         (slot = global index of the node's entry in its end bucket; KP_NONE for EOS)
+//   bent    int2[N]       per bucket entry, what the sweep needs of a PREDECESSOR: {dp, right_id}
+//   bnode   u32[N]        per bucket entry: node index (KP_NONE for BOS)
+//   path    u32[NB]       best path of each sentence, back to front, at the sentence's boundary base
+//   pre     u32[N]        (lattice dump only) predecessor as a bucket slot (KP_NONE = Option::None)
 #pragma once
 #include "kp_common.cuh"
 
@@ -27,7 +30,7 @@ struct kp_chunk {
     uint32_t* nchar;  uint32_t* coff;
     uint4* binfo;
     uint32_t* ncount; uint32_t* noff; uint32_t* bcount; uint32_t* boff; uint32_t* bfill;
-    uint4* rec; uint32_t* slot; int16_t* bright; uint32_t* bnode; int32_t* bdp; uint32_t* pre;
+    uint4* rec; uint2* tgt; int2* bent; uint32_t* bnode; uint32_t* path; uint32_t* pre;
     int32_t* eos_cost; uint32_t* tcount; uint32_t* toff32;
     uint64_t* tok_off;       // [S+1] output (rebased by tok_base)
     kp_token* tokens;        // output
@@ -46,7 +49,8 @@ int kp_launch_lattice_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st
 int kp_launch_bucketize(const kp_chunk& c, cudaStream_t st);
 int kp_launch_viterbi(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
 int kp_launch_pair_count(const kp_chunk& c, cudaStream_t st);
-int kp_launch_backtrace_count(const kp_chunk& c, cudaStream_t st);
+int kp_launch_backtrace_count(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
+int kp_launch_fill_pre(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
 int kp_launch_backtrace_write(const kp_chunk& c, uint64_t tok_base, cudaStream_t st);
 // exclusive scans, n inputs -> n+1 outputs; total (u64) written to *total
 int kp_launch_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint64_t* tmp, uint64_t* total, cudaStream_t st);

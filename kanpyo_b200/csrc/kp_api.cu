@@ -85,7 +85,7 @@ struct kp_tokenizer {
     uint64_t chunk_bytes = 64ull << 20;
     bool count_work = false;
     // chunk scratch
-    DevBuf text, off, nchar, coff, binfo, ncount, noff, bcount, boff, bfill, rec, tgt, bent, bnode, path, pre,
+    DevBuf text, off, nchar, coff, binfo, ncount, noff, bcount, boff, ucount, rcnt, bfill, rec, tgt, red, ndp, bnode, path, pre,
         tcount, toff32, scan_tmp, totals, err;
     // device outputs
     DevBuf d_tok_off, d_tokens, d_eos;
@@ -160,7 +160,9 @@ int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_token
     KP_TRY(t->noff.ensure(sizeof(uint32_t) * (NB + 2)));
     KP_TRY(t->bcount.ensure(sizeof(uint32_t) * (NB + 1)));
     KP_TRY(t->boff.ensure(sizeof(uint32_t) * (NB + 2)));
-    KP_TRY(t->bfill.ensure(sizeof(uint32_t) * (NB + 1)));
+    KP_TRY(t->bfill.ensure(sizeof(uint2) * (NB + 1)));
+    KP_TRY(t->ucount.ensure(sizeof(uint32_t) * (NB + 1)));
+    KP_TRY(t->rcnt.ensure(sizeof(uint32_t) * (NB + 1)));
     KP_TRY(t->scan_tmp.ensure(sizeof(uint64_t) * kp_scan_tmp_elems((uint32_t)NB + 1)));
     c.scan_tmp = t->scan_tmp.as<uint64_t>();
     c.binfo = t->binfo.as<uint4>();
@@ -168,7 +170,9 @@ int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_token
     c.noff = t->noff.as<uint32_t>();
     c.bcount = t->bcount.as<uint32_t>();
     c.boff = t->boff.as<uint32_t>();
-    c.bfill = t->bfill.as<uint32_t>();
+    c.bfill = t->bfill.as<uint2>();
+    c.ucount = t->ucount.as<uint32_t>();
+    c.rcnt = t->rcnt.as<uint32_t>();
 
     KP_LAUNCH(kp_launch_prep_fill(c, d, st));
     KP_CUDA(cudaEventRecord(t->ev[EV_PREP], st));
@@ -186,14 +190,16 @@ int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_token
     const size_t N = c.N;
     KP_TRY(t->rec.ensure(sizeof(uint4) * (N + 1)));
     KP_TRY(t->tgt.ensure(sizeof(uint2) * (N + 1)));
-    KP_TRY(t->bent.ensure(sizeof(int2) * (N + 1)));
+    KP_TRY(t->red.ensure(sizeof(int2) * (N + 1)));
+    KP_TRY(t->ndp.ensure(sizeof(int32_t) * (N + 1)));
     KP_TRY(t->bnode.ensure(sizeof(uint32_t) * (N + 1)));
     KP_TRY(t->path.ensure(sizeof(uint32_t) * (NB + 1)));
     KP_TRY(t->tcount.ensure(sizeof(uint32_t) * (S + 1)));
     KP_TRY(t->toff32.ensure(sizeof(uint32_t) * (S + 2)));
     c.rec = t->rec.as<uint4>();
     c.tgt = t->tgt.as<uint2>();
-    c.bent = t->bent.as<int2>();
+    c.red = t->red.as<int2>();
+    c.ndp = t->ndp.as<int32_t>();
     c.bnode = t->bnode.as<uint32_t>();
     c.path = t->path.as<uint32_t>();
     c.tcount = t->tcount.as<uint32_t>();
@@ -201,8 +207,8 @@ int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_token
 
     KP_LAUNCH(kp_launch_lattice_fill(c, d, st));
     KP_CUDA(cudaEventRecord(t->ev[EV_LATTICE], st));
-    KP_CUDA(cudaMemsetAsync(c.bfill, 0, sizeof(uint32_t) * (NB + 1), st));
-    KP_LAUNCH(kp_launch_bucketize(c, st));
+    KP_CUDA(cudaMemsetAsync(c.bfill, 0, sizeof(uint2) * (NB + 1), st));
+    KP_LAUNCH(kp_launch_bucketize(c, d, st));
     KP_CUDA(cudaEventRecord(t->ev[EV_BUCKET], st));
     KP_LAUNCH(kp_launch_viterbi(c, d, st));
     if (t->count_work) KP_LAUNCH(kp_launch_pair_count(c, st));
@@ -272,7 +278,7 @@ extern "C" void kp_tokenizer_destroy(kp_tokenizer* t) {
     cudaSetDevice(t->device);
     if (t->stream) cudaStreamSynchronize(t->stream);
     DevBuf* bufs[] = {&t->text, &t->off, &t->nchar, &t->coff, &t->binfo, &t->ncount, &t->noff, &t->bcount, &t->boff,
-                      &t->bfill, &t->rec, &t->tgt, &t->bent, &t->bnode, &t->path, &t->pre, &t->tcount, &t->toff32,
+                      &t->bfill, &t->ucount, &t->rcnt, &t->rec, &t->tgt, &t->red, &t->ndp, &t->bnode, &t->path, &t->pre, &t->tcount, &t->toff32,
                       &t->scan_tmp, &t->totals, &t->err, &t->d_tok_off, &t->d_tokens, &t->d_eos};
     for (DevBuf* b : bufs) b->release();
     PinBuf* pins[] = {&t->h_totals, &t->h_tok_off, &t->h_tokens, &t->h_eos, &t->h_misc};
@@ -456,23 +462,22 @@ extern "C" int kp_lattice_dump(kp_tokenizer* t, const uint8_t* utf8, uint64_t le
         c.N = N;
         c.rec = t->rec.as<uint4>();
         c.tgt = t->tgt.as<uint2>();
-        c.bent = t->bent.as<int2>();
+        c.ndp = t->ndp.as<int32_t>();
+        c.bnode = t->bnode.as<uint32_t>();
         c.boff = t->boff.as<uint32_t>();
-        c.eos_cost = t->d_eos.as<int32_t>();
         c.pre = t->pre.as<uint32_t>();
         KP_TRY(kp_launch_fill_pre(c, t->dict->view, t->stream));
         KP_CUDA(cudaStreamSynchronize(t->stream));
     }
     std::vector<uint4> rec(N), binfo(NB);
     std::vector<uint32_t> bnode(N), pre(N);
-    std::vector<uint2> tgt(N);
-    std::vector<int2> bent(N);
+    std::vector<int32_t> ndp(N);
     KP_CUDA(cudaMemcpy(rec.data(), t->rec.p, sizeof(uint4) * N, cudaMemcpyDeviceToHost));
     KP_CUDA(cudaMemcpy(binfo.data(), t->binfo.p, sizeof(uint4) * NB, cudaMemcpyDeviceToHost));
-    KP_CUDA(cudaMemcpy(tgt.data(), t->tgt.p, sizeof(uint2) * N, cudaMemcpyDeviceToHost));
+
     KP_CUDA(cudaMemcpy(bnode.data(), t->bnode.p, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost));
     KP_CUDA(cudaMemcpy(pre.data(), t->pre.p, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost));
-    KP_CUDA(cudaMemcpy(bent.data(), t->bent.p, sizeof(int2) * N, cudaMemcpyDeviceToHost));
+    KP_CUDA(cudaMemcpy(ndp.data(), t->ndp.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost));
     t->lattice_nodes.assign((size_t)N + 1, kp_lattice_node{});
     kp_lattice_node& bos = t->lattice_nodes[0];
     bos.id = 0;
@@ -491,7 +496,7 @@ extern "C" int kp_lattice_dump(kp_tokenizer* t, const uint8_t* utf8, uint64_t le
         o.left_id = (int16_t)(x.z & 0xFFFF);
         o.right_id = (int16_t)(x.z >> 16);
         o.cost = (int16_t)(x.w & 0xFFFF);
-        o.dp = kind == KP_CLASS_DUMMY ? r.eos_cost[0] : bent[tgt[i].y].x;
+        o.dp = ndp[i];
         o.pre = pre[i] == KP_NONE ? -1 : (bnode[pre[i]] == KP_NONE ? 0 : (int32_t)bnode[pre[i]] + 1);
     }
     out->n_nodes = (uint64_t)N + 1;
@@ -507,18 +512,18 @@ extern "C" int kp_da_common_prefix(kp_tokenizer* t, const uint8_t* utf8, uint64_
     const uint32_t dcap = (uint32_t)std::min<uint64_t>(cap, 1u << 20);
     KP_TRY(t->text.ensure(len + 16));
     KP_TRY(t->rec.ensure(sizeof(int64_t) * (dcap + 1)));
-    KP_TRY(t->bent.ensure(sizeof(uint64_t) * (dcap + 1)));
+    KP_TRY(t->red.ensure(sizeof(uint64_t) * (dcap + 1)));
     KP_TRY(t->err.ensure(sizeof(uint32_t) * 2));
     if (len) KP_CUDA(cudaMemcpyAsync(t->text.p, utf8, len, cudaMemcpyHostToDevice, st));
     KP_TRY(kp_launch_common_prefix(t->dict->view, t->text.as<uint8_t>(), (uint32_t)len, expand_dup, t->rec.as<int64_t>(),
-                                   t->bent.as<uint64_t>(), dcap, t->err.as<uint32_t>(), st));
+                                   t->red.as<uint64_t>(), dcap, t->err.as<uint32_t>(), st));
     uint32_t hn = 0;
     KP_CUDA(cudaMemcpyAsync(&hn, t->err.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaStreamSynchronize(st));
     const uint32_t m = std::min(hn, dcap);
     if (m) {
         KP_CUDA(cudaMemcpy(ids, t->rec.p, sizeof(int64_t) * m, cudaMemcpyDeviceToHost));
-        KP_CUDA(cudaMemcpy(byte_lens, t->bent.p, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost));
+        KP_CUDA(cudaMemcpy(byte_lens, t->red.p, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost));
     }
     *n = hn;
     return KP_OK;

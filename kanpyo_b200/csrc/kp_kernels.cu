@@ -272,7 +272,8 @@ __global__ void __launch_bounds__(PREP_THREADS) kp_prep_count(const uint8_t* __r
 __global__ void __launch_bounds__(PREP_THREADS) kp_prep_fill(const uint8_t* __restrict__ text,
                                                              const uint64_t* __restrict__ off, uint64_t base, uint32_t S,
                                                              const uint32_t* __restrict__ coff, kp_ddict d,
-                                                             uint4* __restrict__ binfo, uint32_t* __restrict__ bcount) {
+                                                             uint4* __restrict__ binfo, uint32_t* __restrict__ bcount,
+                                                             uint32_t* __restrict__ ucount) {
     uint32_t s = (blockIdx.x * PREP_THREADS + threadIdx.x) >> 5;
     if (s >= S) return;
     const uint32_t lane = lane_id();
@@ -297,12 +298,14 @@ __global__ void __launch_bounds__(PREP_THREADS) kp_prep_fill(const uint8_t* __re
             uint32_t p = run + __popc(m & lanemask_lt());
             binfo[bb + p] = make_uint4(i, hi, 0u, cat);
             bcount[bb + p] = p == 0 ? 1u : 0u;    // BOS sits in edges[0] (lattice.rs:156-164)
+            ucount[bb + p] = 0u;
         }
         run += __popc(m);
     }
     if (lane == 0) {
         binfo[bb + n] = make_uint4(hi, hi, bb + n + 1, 0xFFFFu);   // EOS boundary (lattice.rs:165-175)
         bcount[bb + n] = n == 0 ? 1u : 0u;
+        ucount[bb + n] = 0u;
     }
     __syncwarp();
     // backward: end of the same-class run each char belongs to (lattice.rs:69-84), capped at 1024 chars
@@ -335,7 +338,7 @@ int kp_launch_prep_count(const kp_chunk& c, cudaStream_t st) {
 int kp_launch_prep_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
     if (c.S == 0) return 0;
     uint32_t blocks = (uint32_t)(((uint64_t)c.S * 32 + PREP_THREADS - 1) / PREP_THREADS);
-    kp_prep_fill<<<blocks, PREP_THREADS, 0, st>>>(c.text, c.off, c.base, c.S, c.coff, d, c.binfo, c.bcount);
+    kp_prep_fill<<<blocks, PREP_THREADS, 0, st>>>(c.text, c.off, c.base, c.S, c.coff, d, c.binfo, c.bcount, c.ucount);
     return kp_launch_check("kp_prep_fill");
 }
 
@@ -350,6 +353,7 @@ template <bool FILL, bool WORK>
 __global__ void __launch_bounds__(LAT_THREADS) kp_lattice_walk(const uint8_t* __restrict__ text,
                                                           const uint4* __restrict__ binfo, uint32_t NB, kp_ddict d,
                                                           uint32_t* __restrict__ ncount, uint32_t* __restrict__ bcount,
+                                                          uint32_t* __restrict__ ucount,
                                                           const uint32_t* __restrict__ noff, uint4* __restrict__ rec,
                                                           uint64_t* __restrict__ totals) {
     uint32_t b = blockIdx.x * LAT_THREADS + threadIdx.x;
@@ -408,6 +412,7 @@ __global__ void __launch_bounds__(LAT_THREADS) kp_lattice_walk(const uint8_t* __
                 if (!FILL) {
                     total += ci.unk_count;
                     atomicAdd(&bcount[bi.z], ci.unk_count);
+                    atomicAdd(&ucount[bi.z], ci.unk_count);
                 } else {
                     uint32_t ulen = bi.z - b;
                     for (uint32_t j = 0; j < ci.unk_count; j++) {
@@ -435,73 +440,103 @@ int kp_launch_lattice_count(const kp_chunk& c, const kp_ddict& d, bool count_wor
     if (c.NB == 0) return 0;
     uint32_t blocks = (c.NB + LAT_THREADS - 1) / LAT_THREADS;
     if (count_work)
-        kp_lattice_walk<false, true><<<blocks, LAT_THREADS, 0, st>>>(c.text, c.binfo, c.NB, d, c.ncount, c.bcount, nullptr,
-                                                                nullptr, c.totals);
+        kp_lattice_walk<false, true><<<blocks, LAT_THREADS, 0, st>>>(c.text, c.binfo, c.NB, d, c.ncount, c.bcount, c.ucount,
+                                                                nullptr, nullptr, c.totals);
     else
-        kp_lattice_walk<false, false><<<blocks, LAT_THREADS, 0, st>>>(c.text, c.binfo, c.NB, d, c.ncount, c.bcount, nullptr,
-                                                                 nullptr, c.totals);
+        kp_lattice_walk<false, false><<<blocks, LAT_THREADS, 0, st>>>(c.text, c.binfo, c.NB, d, c.ncount, c.bcount, c.ucount,
+                                                                 nullptr, nullptr, c.totals);
     return kp_launch_check("kp_lattice_walk<count>");
 }
 
 int kp_launch_lattice_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
     if (c.NB == 0) return 0;
     uint32_t blocks = (c.NB + LAT_THREADS - 1) / LAT_THREADS;
-    kp_lattice_walk<true, false><<<blocks, LAT_THREADS, 0, st>>>(c.text, c.binfo, c.NB, d, nullptr, nullptr, c.noff, c.rec,
-                                                            c.totals);
+    kp_lattice_walk<true, false><<<blocks, LAT_THREADS, 0, st>>>(c.text, c.binfo, c.NB, d, nullptr, nullptr, nullptr, c.noff,
+                                                            c.rec, c.totals);
     return kp_launch_check("kp_lattice_walk<fill>");
 }
 
 // =================================================================================================
-// Bucketize: stable placement of every node into its end bucket (the reference's edges[end] lists,
-// ascending node index).  One warp per sentence walks its nodes in order, 32 at a time, and writes
-// the two packed views the Viterbi sweep reads: tgt[node] and bent[bucket slot].
+// Bucketize.  One warp per sentence walks its nodes in order, 32 at a time, and builds
+//   * bnode: the reference's edges[end] lists (stable: ascending node index), used by the back-trace;
+//   * red / rcnt / tgt: the REDUCED buckets the Viterbi sweep scans (layout in kp_kernels.cuh).
+// Why reduced: every start position inside a same-class run emits the class's unknown nodes, and
+// they all end at the run's end -- buckets of 100+ entries that differ only in dp.  A successor only
+// ever needs min(dp) per distinct (right_id); for unknown nodes the distinct ids are known
+// statically (the ids of the class of the char before the boundary), so they get one shared slot
+// each and the sweep min-merges into it.  The minimum VALUE is unchanged, and the back-trace picks
+// the first predecessor attaining it from the full list, so results are bit-identical.
 // =================================================================================================
 constexpr int SENT_THREADS = 128;   // 4 sentences per CTA
 
 __global__ void __launch_bounds__(SENT_THREADS) kp_bucketize(uint32_t S, const uint32_t* __restrict__ coff,
                                                              const uint32_t* __restrict__ noff,
                                                              const uint32_t* __restrict__ boff,
-                                                             const uint4* __restrict__ rec, uint32_t* __restrict__ bfill,
-                                                             uint2* __restrict__ tgt, int2* __restrict__ bent,
+                                                             const uint32_t* __restrict__ bcount,
+                                                             const uint32_t* __restrict__ ucount,
+                                                             const uint4* __restrict__ binfo,
+                                                             const uint4* __restrict__ rec, kp_ddict d,
+                                                             uint2* __restrict__ bfill, uint32_t* __restrict__ rcnt,
+                                                             uint2* __restrict__ tgt, int2* __restrict__ red,
                                                              uint32_t* __restrict__ bnode) {
     uint32_t s = (blockIdx.x * SENT_THREADS + threadIdx.x) >> 5;
     if (s >= S) return;
     const uint32_t lane = lane_id();
     const uint32_t bb = coff[s] + s, n = coff[s + 1] - coff[s];
     const uint32_t n0 = noff[bb], n1 = noff[bb + n];   // nodes before the EOS node (which is node n1)
+    // reduced bucket sizes: known nodes (+BOS) + the unknown ids of the preceding char's class
+    for (uint32_t p = lane; p <= n; p += 32) {
+        const uint32_t b = bb + p;
+        const uint32_t uc = ucount[b];
+        uint32_t r = bcount[b] - uc;
+        if (uc) r += d.catinfo[binfo[b - 1].w & 0xFFu].unk_count;   // uc > 0 implies p > 0
+        rcnt[b] = r;
+    }
     if (lane == 0) {
         uint32_t q = boff[bb];                          // BOS: dp None -> unwrap_or(0) (lattice.rs:127)
-        bent[q] = make_int2(0, 0);
+        red[q] = make_int2(0, 0);
         bnode[q] = KP_NONE;
-        tgt[n1] = make_uint2(0u, KP_NONE);              // EOS: morph (0,0,0), no bucket entry needed
+        tgt[n1] = make_uint2(0u, KP_NONE);              // EOS: morph (0,0,0), ends nowhere
     }
     for (uint32_t i0 = n0; i0 < n1; i0 += 32) {
         uint32_t i = i0 + lane;
         bool valid = i < n1;
         uint4 r = valid ? rec[i] : make_uint4(0, 0, 0, 0);
         uint32_t e = valid ? r.y + (r.w >> 16) : KP_NONE;   // end boundary = start + char_len (lattice.rs:187,200)
+        const bool known = valid && (r.x >> KP_KIND_SHIFT) == KP_CLASS_KNOWN;
         uint32_t m = __match_any_sync(KP_FULL, e);
+        const uint32_t km = m & __ballot_sync(KP_FULL, known);
         uint32_t leader = (uint32_t)__ffs(m) - 1;
-        uint32_t old = 0;
+        uint2 old = make_uint2(0, 0);
         if (valid && lane == leader) {
             old = bfill[e];
-            bfill[e] = old + (uint32_t)__popc(m);
+            bfill[e] = make_uint2(old.x + (uint32_t)__popc(m), old.y + (uint32_t)__popc(km));
         }
-        old = __shfl_sync(KP_FULL, old, leader);
+        old.x = __shfl_sync(KP_FULL, old.x, leader);
+        old.y = __shfl_sync(KP_FULL, old.y, leader);
         if (valid) {
-            uint32_t q = boff[e] + old + (uint32_t)__popc(m & lanemask_lt()) + (e == bb ? 1u : 0u);
-            tgt[i] = make_uint2((r.z & 0xFFFFu) | (r.w << 16), q);
-            bent[q] = make_int2(KP_INF, (int)((r.z >> 16) * 2u));   // right_id as a byte offset into a conn row
-            bnode[q] = i;
+            const uint32_t first = e == bb ? 1u : 0u;       // BOS occupies slot 0 of the first bucket
+            const uint32_t base = boff[e];
+            bnode[base + first + old.x + (uint32_t)__popc(m & lanemask_lt())] = i;
+            uint32_t slot;
+            if (known) {
+                slot = base + first + old.y + (uint32_t)__popc(km & lanemask_lt());
+            } else {                                        // shared slot of (end boundary, unknown id)
+                const uint32_t cat = binfo[r.y].w & 0xFFu;  // class of the node's first char = of all its chars
+                slot = base + (bcount[e] - ucount[e]) + ((r.x & KP_ID_MASK) - (uint32_t)d.catinfo[cat].unk_first);
+            }
+            red[slot] = make_int2(KP_INF, (int)((r.z >> 16) * 2u));   // right_id as a byte offset into a conn row
+            tgt[i] = make_uint2((r.z & 0xFFFFu) | (r.w << 16), slot);
         }
         __syncwarp();
     }
 }
 
-int kp_launch_bucketize(const kp_chunk& c, cudaStream_t st) {
+int kp_launch_bucketize(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
     if (c.S == 0) return 0;
     uint32_t blocks = (uint32_t)(((uint64_t)c.S * 32 + SENT_THREADS - 1) / SENT_THREADS);
-    kp_bucketize<<<blocks, SENT_THREADS, 0, st>>>(c.S, c.coff, c.noff, c.boff, c.rec, c.bfill, c.tgt, c.bent, c.bnode);
+    kp_bucketize<<<blocks, SENT_THREADS, 0, st>>>(c.S, c.coff, c.noff, c.boff, c.bcount, c.ucount, c.binfo, c.rec, d,
+                                                  c.bfill, c.rcnt, c.tgt, c.red, c.bnode);
     return kp_launch_check("kp_bucketize");
 }
 
@@ -510,14 +545,14 @@ int kp_launch_bucketize(const kp_chunk& c, cudaStream_t st) {
 //
 // A warp carries 4 sentences, 8 lanes each, and steps all of them boundary by boundary with
 // warp-uniform loop bounds, so the four groups share every issued instruction.  Lanes hold the nodes
-// STARTING at the boundary (targets); each lane folds the nodes ENDING there (predecessors) with one
-// DPX add-min per pair:   best = min(best, dp[j] + conn(right_j, left_i))          connection.rs:12-14
-//   dp[i] = min(best + cost_i, INF), kept only if < INF                            lattice.rs:127-139
+// STARTING at the boundary (targets); each lane folds the boundary's reduced bucket (predecessors)
+// with one DPX add-min per pair:   best = min(best, dp[j] + conn(right_j, left_i))   connection.rs:12-14
+//   dp[i] = min(best + cost_i, INF), kept only if < INF                              lattice.rs:127-139
 // Out-of-range predecessor slots are clamped to the bucket's last entry: a duplicate never changes a
 // minimum.  The argmin (pre_nodes) is NOT tracked here: the back-trace recomputes it for the ~30
 // nodes per sentence that lie on the best path (first j attaining dp[i], which is what the strict '<'
-// update of lattice.rs:136 selects).  dp travels from a target to its end bucket through
-// bent[slot].x; the __syncwarp orders that store before the next boundary's loads.
+// update of lattice.rs:136 selects).  dp goes to ndp[i] and is min-merged into the node's reduced
+// slot; the __syncwarp orders those stores before the next boundary's loads.
 // =================================================================================================
 constexpr int VIT_GROUP = 8;
 constexpr int VIT_THREADS = 128;
@@ -531,8 +566,9 @@ __device__ __forceinline__ int ld_conn(const char* p) {
 __global__ void __launch_bounds__(VIT_THREADS) kp_viterbi(uint32_t S, const uint32_t* __restrict__ coff,
                                                           const uint32_t* __restrict__ noff,
                                                           const uint32_t* __restrict__ boff,
-                                                          const uint2* __restrict__ tgt, int2* bent,
-                                                          int32_t* __restrict__ eos_cost,
+                                                          const uint32_t* __restrict__ rcnt,
+                                                          const uint2* __restrict__ tgt, int2* red,
+                                                          int32_t* __restrict__ ndp, int32_t* __restrict__ eos_cost,
                                                           const int16_t* __restrict__ conn, uint32_t conn_row) {
     const uint32_t s = (blockIdx.x * VIT_THREADS + threadIdx.x) / VIT_GROUP;
     const uint32_t l = threadIdx.x & (VIT_GROUP - 1);
@@ -543,88 +579,98 @@ __global__ void __launch_bounds__(VIT_THREADS) kp_viterbi(uint32_t S, const uint
         n = coff[s + 1] - coff[s];
     }
     const uint32_t steps = __reduce_max_sync(KP_FULL, has ? n + 1 : 0u);
-    uint32_t t0 = 0, q0 = 0, t1n = 0, q1n = 0;
+    uint32_t t0 = 0, t1n = 0, rbn = 0, rn = 0;
     if (has) {
         t0 = noff[bb];
-        q0 = boff[bb];
         t1n = noff[bb + 1];
-        q1n = boff[bb + 1];
+        rbn = boff[bb];
+        rn = rcnt[bb];
     }
     const size_t row_bytes = (size_t)conn_row * 2;
     for (uint32_t p = 0; p < steps; p++) {
         const bool act = has && p <= n;
-        const uint32_t t1 = act ? t1n : t0, q1 = act ? q1n : q0;
+        const uint32_t t1 = act ? t1n : t0, rb = rbn, R = act ? rn : 0u;
         if (has && p < n) {                       // bounds of the next boundary, off the critical path
             t1n = noff[bb + p + 2];
-            q1n = boff[bb + p + 2];
+            rbn = boff[bb + p + 1];
+            rn = rcnt[bb + p + 1];
         }
-        const uint32_t T = t1 - t0, P = q1 - q0;
-        const uint32_t Tmax = __reduce_max_sync(KP_FULL, T), Pmax = __reduce_max_sync(KP_FULL, P);
-        const uint32_t qb = P ? q0 : 0u, qlast = P ? q1 - 1 : 0u;    // P == 0: harmless reads of entry 0
+        const uint32_t T = t1 - t0;
+        const uint32_t Tmax = __reduce_max_sync(KP_FULL, T), Rmax = __reduce_max_sync(KP_FULL, R);
+        const uint32_t qb = R ? rb : 0u, qlast = R ? rb + R - 1 : 0u;    // R == 0: harmless reads of entry 0
         for (uint32_t tc = 0; tc < Tmax; tc += VIT_GROUP) {
             const bool tv = tc + l < T;
             const uint2 tg = tv ? tgt[t0 + tc + l] : make_uint2(0u, KP_NONE);
             const char* crow = (const char*)conn + (size_t)(tg.x & 0xFFFFu) * row_bytes;
             int best = INT_MAX;
-            for (uint32_t jj = 0; jj < Pmax; jj += 4) {
+            for (uint32_t jj = 0; jj < Rmax; jj += 4) {
 #pragma unroll
                 for (uint32_t u = 0; u < 4; u++) {
-                    const int2 e = bent[min(qb + jj + u, qlast)];
+                    const int2 e = red[min(qb + jj + u, qlast)];
                     best = __viaddmin_s32(e.x, ld_conn(crow + (uint32_t)e.y), best);
                 }
             }
             if (tv) {
                 int dp = KP_INF;
-                if (P) dp = min(best + (int)(int16_t)(tg.x >> 16), KP_INF);
+                if (R) dp = min(best + (int)(int16_t)(tg.x >> 16), KP_INF);
+                ndp[t0 + tc + l] = dp;
                 if (tg.y == KP_NONE) eos_cost[s] = dp;
-                else bent[tg.y].x = dp;
+                else red[tg.y].x = min(red[tg.y].x, dp);     // shared slots keep the minimum
             }
         }
         __syncwarp();
         t0 = t1;
-        q0 = q1;
     }
 }
 
 int kp_launch_viterbi(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
     if (c.S == 0) return 0;
     uint32_t blocks = (uint32_t)(((uint64_t)c.S * VIT_GROUP + VIT_THREADS - 1) / VIT_THREADS);
-    kp_viterbi<<<blocks, VIT_THREADS, 0, st>>>(c.S, c.coff, c.noff, c.boff, c.tgt, c.bent, c.eos_cost, d.conn, d.conn_row);
+    kp_viterbi<<<blocks, VIT_THREADS, 0, st>>>(c.S, c.coff, c.noff, c.boff, c.rcnt, c.tgt, c.red, c.ndp, c.eos_cost,
+                                               d.conn, d.conn_row);
     return kp_launch_check("kp_viterbi");
 }
 
-// pre_nodes[i] for EVERY node (lattice.rs:136-139), recomputed from the dp values: the first
-// predecessor attaining dp[i].  Only the lattice dump needs it (one thread per node).
-__device__ __forceinline__ uint32_t kp_first_argmin(const int2* __restrict__ bent, uint32_t q0, uint32_t q1,
+// First predecessor of a node attaining its dp, scanned in the reference's list order
+// (edges[start], ascending node index): pre_nodes[i] of lattice.rs:136-139.
+__device__ __forceinline__ uint32_t kp_first_argmin(const uint32_t* __restrict__ bnode, const int32_t* __restrict__ ndp,
+                                                    const uint4* __restrict__ rec, uint32_t q0, uint32_t q1,
                                                     const char* crow, int want) {
     for (uint32_t j = q0; j < q1; j++) {
-        const int2 e = bent[j];
-        if (e.x + ld_conn(crow + (uint32_t)e.y) == want) return j;
+        const uint32_t nd = bnode[j];
+        int dpj = 0;
+        uint32_t right = 0;                      // BOS: dp None -> 0, morph (0,0,0)
+        if (nd != KP_NONE) {
+            dpj = ndp[nd];
+            right = rec[nd].z >> 16;
+        }
+        if (dpj + ld_conn(crow + right * 2u) == want) return j;
     }
     return KP_NONE;
 }
 
+// pre_nodes[i] for EVERY node, recomputed from the dp values.  Only the lattice dump needs it.
 __global__ void __launch_bounds__(256) kp_fill_pre(uint32_t N, const uint4* __restrict__ rec,
-                                                   const uint2* __restrict__ tgt, const int2* __restrict__ bent,
-                                                   const uint32_t* __restrict__ boff,
-                                                   const int32_t* __restrict__ eos_cost, uint32_t* __restrict__ pre,
+                                                   const uint2* __restrict__ tgt, const int32_t* __restrict__ ndp,
+                                                   const uint32_t* __restrict__ bnode,
+                                                   const uint32_t* __restrict__ boff, uint32_t* __restrict__ pre,
                                                    const int16_t* __restrict__ conn, uint32_t conn_row) {
     uint32_t i = blockIdx.x * 256 + threadIdx.x;
     if (i >= N) return;
     const uint2 tg = tgt[i];
     const uint32_t b = rec[i].y;
-    const int dp = tg.y == KP_NONE ? eos_cost[0] : bent[tg.y].x;     // dump runs on a single sentence
+    const int dp = ndp[i];
     uint32_t pr = KP_NONE;
     if (dp < KP_INF)
-        pr = kp_first_argmin(bent, boff[b], boff[b + 1], (const char*)conn + (size_t)(tg.x & 0xFFFFu) * conn_row * 2,
+        pr = kp_first_argmin(bnode, ndp, rec, boff[b], boff[b + 1],
+                             (const char*)conn + (size_t)(tg.x & 0xFFFFu) * conn_row * 2,
                              dp - (int)(int16_t)(tg.x >> 16));
     pre[i] = pr;
 }
 
 int kp_launch_fill_pre(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
     if (c.N == 0) return 0;
-    kp_fill_pre<<<(c.N + 255) / 256, 256, 0, st>>>(c.N, c.rec, c.tgt, c.bent, c.boff, c.eos_cost, c.pre, d.conn,
-                                                   d.conn_row);
+    kp_fill_pre<<<(c.N + 255) / 256, 256, 0, st>>>(c.N, c.rec, c.tgt, c.ndp, c.bnode, c.boff, c.pre, d.conn, d.conn_row);
     return kp_launch_check("kp_fill_pre");
 }
 
@@ -645,57 +691,88 @@ int kp_launch_pair_count(const kp_chunk& c, cudaStream_t st) {
 }
 
 // =================================================================================================
-// Back-trace (lattice.rs:144-153) + Node -> Token (tokenizer.rs:22-43).  One thread per sentence.
-// Pass 1 walks from the EOS node, recomputing each predecessor as the first j with
-// dp[j] + conn + cost == dp[i], and parks the path (node indices, back to front) in `path`;
+// Back-trace (lattice.rs:144-153) + Node -> Token (tokenizer.rs:22-43).  8 lanes per sentence.
+// Pass 1 walks from the EOS node; the lanes test 8 candidate predecessors at a time for
+// dp[j] + conn + cost == dp[i] and a ballot picks the first (list order), which is the predecessor the
+// reference's strict '<' update keeps.  The path (node indices, back to front) is parked in `path`;
 // pass 2 (after the scan of the path lengths) writes the tokens front to back.
 // =================================================================================================
-__global__ void __launch_bounds__(128) kp_backtrace_find(uint32_t S, const uint32_t* __restrict__ coff,
-                                                         const uint32_t* __restrict__ noff,
-                                                         const uint32_t* __restrict__ boff,
-                                                         const uint4* __restrict__ rec, const uint2* __restrict__ tgt,
-                                                         const int2* __restrict__ bent,
-                                                         const uint32_t* __restrict__ bnode,
-                                                         const int32_t* __restrict__ eos_cost,
-                                                         const int16_t* __restrict__ conn, uint32_t conn_row,
-                                                         uint32_t* __restrict__ path, uint32_t* __restrict__ tcount) {
-    uint32_t s = blockIdx.x * 128 + threadIdx.x;
-    if (s >= S) return;
+constexpr int BT_THREADS = 128;
+constexpr int BT_GROUP = 8;
+
+__global__ void __launch_bounds__(BT_THREADS) kp_backtrace_find(uint32_t S, const uint32_t* __restrict__ coff,
+                                                                const uint32_t* __restrict__ noff,
+                                                                const uint32_t* __restrict__ boff,
+                                                                const uint4* __restrict__ rec,
+                                                                const uint2* __restrict__ tgt,
+                                                                const int32_t* __restrict__ ndp,
+                                                                const uint32_t* __restrict__ bnode,
+                                                                const int16_t* __restrict__ conn, uint32_t conn_row,
+                                                                uint32_t* __restrict__ path,
+                                                                uint32_t* __restrict__ tcount) {
+    const uint32_t s = (blockIdx.x * BT_THREADS + threadIdx.x) / BT_GROUP;
+    if (s >= S) return;                          // whole groups leave together
+    const uint32_t l = threadIdx.x & (BT_GROUP - 1), gshift = lane_id() & ~(uint32_t)(BT_GROUP - 1);
+    const uint32_t gmask = ((1u << BT_GROUP) - 1u) << gshift;
     const uint32_t bb = coff[s] + s, n = coff[s + 1] - coff[s];
     uint32_t cur = noff[bb + n];                 // `self.nodes.len() - 1`: the EOS node
     uint32_t cnt = 0;
-    int dp = eos_cost[s];
     while (true) {
+        const int dp = ndp[cur];
         if (dp >= KP_INF) break;                 // pre_nodes[pos] is None: no total < INF was ever seen
         const uint2 tg = tgt[cur];
         const uint32_t b = rec[cur].y;
-        const uint32_t q = kp_first_argmin(bent, boff[b], boff[b + 1],
-                                           (const char*)conn + (size_t)(tg.x & 0xFFFFu) * conn_row * 2,
-                                           dp - (int)(int16_t)(tg.x >> 16));
-        if (q == KP_NONE) break;                 // unreachable for a consistent dp table
-        path[bb + cnt] = cur;                    // path length <= n + 1 = boundaries of the sentence
+        const uint32_t q0 = boff[b], q1 = boff[b + 1];
+        const char* crow = (const char*)conn + (size_t)(tg.x & 0xFFFFu) * conn_row * 2;   // connection.rs:12-14
+        const int want = dp - (int)(int16_t)(tg.x >> 16);
+        uint32_t found = KP_NONE, next = KP_NONE;
+        for (uint32_t j0 = q0; j0 < q1; j0 += BT_GROUP) {
+            const uint32_t j = j0 + l;
+            bool ok = false;
+            uint32_t nd = KP_NONE;
+            if (j < q1) {
+                nd = bnode[j];
+                int dpj = 0;
+                uint32_t right = 0;              // BOS: dp None -> 0, morph (0,0,0)
+                if (nd != KP_NONE) {
+                    dpj = ndp[nd];
+                    right = rec[nd].z >> 16;
+                }
+                ok = dpj + ld_conn(crow + right * 2u) == want;
+            }
+            const uint32_t m = (__ballot_sync(gmask, ok) >> gshift) & ((1u << BT_GROUP) - 1u);
+            if (m) {                             // first match in list order
+                const uint32_t w = (uint32_t)__ffs(m) - 1;
+                found = j0 + w;
+                next = __shfl_sync(gmask, nd, gshift + w);
+                break;
+            }
+        }
+        if (found == KP_NONE) break;             // unreachable for a consistent dp table
+        if (l == 0) path[bb + cnt] = cur;        // path length <= n + 1 = boundaries of the sentence
         cnt++;
-        cur = bnode[q];
+        cur = next;
         if (cur == KP_NONE) break;               // reached BOS, which has no predecessor and is not emitted
-        dp = bent[q].x;
     }
-    tcount[s] = cnt;
+    if (l == 0) tcount[s] = cnt;
 }
 
-__global__ void __launch_bounds__(128) kp_backtrace_emit(uint32_t S, const uint32_t* __restrict__ coff,
-                                                         const uint4* __restrict__ rec,
-                                                         const uint4* __restrict__ binfo,
-                                                         const uint32_t* __restrict__ path,
-                                                         const uint32_t* __restrict__ toff, uint64_t tok_base,
-                                                         uint64_t* __restrict__ tok_off, kp_token* __restrict__ tokens) {
-    uint32_t s = blockIdx.x * 128 + threadIdx.x;
+__global__ void __launch_bounds__(BT_THREADS) kp_backtrace_emit(uint32_t S, const uint32_t* __restrict__ coff,
+                                                                const uint4* __restrict__ rec,
+                                                                const uint4* __restrict__ binfo,
+                                                                const uint32_t* __restrict__ path,
+                                                                const uint32_t* __restrict__ toff, uint64_t tok_base,
+                                                                uint64_t* __restrict__ tok_off,
+                                                                kp_token* __restrict__ tokens) {
+    const uint32_t s = (blockIdx.x * BT_THREADS + threadIdx.x) / BT_GROUP;
+    const uint32_t l = threadIdx.x & (BT_GROUP - 1);
     if (s > S) return;
-    tok_off[s] = tok_base + toff[s];
+    if (l == 0) tok_off[s] = tok_base + toff[s];
     if (s == S) return;
     const uint32_t bb = coff[s] + s;
     const uint32_t sent_byte0 = binfo[bb].x;     // for n == 0 this is the EOS boundary: also the sentence start
     const uint32_t w0 = toff[s], cnt = toff[s + 1] - w0;
-    for (uint32_t k = 0; k < cnt; k++) {
+    for (uint32_t k = l; k < cnt; k += BT_GROUP) {
         const uint4 r = rec[path[bb + cnt - 1 - k]];
         const uint32_t kind = r.x >> KP_KIND_SHIFT;
         kp_token t;
@@ -711,13 +788,13 @@ __global__ void __launch_bounds__(128) kp_backtrace_emit(uint32_t S, const uint3
 
 int kp_launch_backtrace_count(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
     if (c.S == 0) return 0;
-    kp_backtrace_find<<<(c.S + 127) / 128, 128, 0, st>>>(c.S, c.coff, c.noff, c.boff, c.rec, c.tgt, c.bent, c.bnode,
-                                                         c.eos_cost, d.conn, d.conn_row, c.path, c.tcount);
+    kp_backtrace_find<<<(uint32_t)(((uint64_t)c.S * BT_GROUP + BT_THREADS - 1) / BT_THREADS), BT_THREADS, 0, st>>>(c.S, c.coff, c.noff, c.boff, c.rec, c.tgt, c.ndp, c.bnode,
+                                                         d.conn, d.conn_row, c.path, c.tcount);
     return kp_launch_check("kp_backtrace_find");
 }
 
 int kp_launch_backtrace_write(const kp_chunk& c, uint64_t tok_base, cudaStream_t st) {
-    kp_backtrace_emit<<<(c.S + 1 + 127) / 128, 128, 0, st>>>(c.S, c.coff, c.rec, c.binfo, c.path, c.toff32, tok_base,
+    kp_backtrace_emit<<<(uint32_t)(((uint64_t)(c.S + 1) * BT_GROUP + BT_THREADS - 1) / BT_THREADS), BT_THREADS, 0, st>>>(c.S, c.coff, c.rec, c.binfo, c.path, c.toff32, tok_base,
                                                              c.tok_off, c.tokens);
     return kp_launch_check("kp_backtrace_emit");
 }

@@ -9,10 +9,19 @@
 //   ncount/noff u32[NB+1] nodes STARTING at each boundary (count / exclusive scan) = reference insertion order
 //   bcount/boff u32[NB+1] nodes ENDING at each boundary (+BOS at p=0)  = the reference's `edges` buckets
 //   rec     uint4[N]      node {id|class<<30, start boundary, left|right<<16, cost|char_len<<16}
-//   tgt     uint2[N]      per node, what the Viterbi sweep needs of a TARGET: {left | cost<<16, bucket slot}
-//                         (slot = global index of the node's entry in its end bucket; KP_NONE for EOS)
-//   bent    int2[N]       per bucket entry, what the sweep needs of a PREDECESSOR: {dp, right_id}
-//   bnode   u32[N]        per bucket entry: node index (KP_NONE for BOS)
+//   ucount  u32[NB]       UNKNOWN nodes ending at each boundary (subset of bcount)
+//   bnode   u32[N]        the reference's `edges` lists: per bucket entry (ascending node index) the node
+//                         index (KP_NONE for BOS); bucket of boundary b = [boff[b], boff[b+1])
+//   red     int2[N]       REDUCED buckets, what the Viterbi sweep scans as predecessors: {min dp, right_id*2}.
+//                         Region of boundary b = [boff[b], boff[b] + rcnt[b]): one entry per known node
+//                         ending at b (BOS first at a sentence's first boundary), then one entry per
+//                         unknown-morph id of the class of the char before b, shared by ALL unknown nodes
+//                         with that id ending at b (they have the same right_id; only their minimum dp
+//                         can matter to a successor)
+//   rcnt    u32[NB]       entries in the reduced bucket of each boundary
+//   tgt     uint2[N]      per node, what the sweep needs of a TARGET: {left | cost<<16, reduced slot}
+//                         (global index into red; KP_NONE for EOS)
+//   ndp     i32[N]        dp of every node (the back-trace and the lattice dump read it)
 //   path    u32[NB]       best path of each sentence, back to front, at the sentence's boundary base
 //   pre     u32[N]        (lattice dump only) predecessor as a bucket slot (KP_NONE = Option::None)
 #pragma once
@@ -29,8 +38,9 @@ struct kp_chunk {
     // scratch (device)
     uint32_t* nchar;  uint32_t* coff;
     uint4* binfo;
-    uint32_t* ncount; uint32_t* noff; uint32_t* bcount; uint32_t* boff; uint32_t* bfill;
-    uint4* rec; uint2* tgt; int2* bent; uint32_t* bnode; uint32_t* path; uint32_t* pre;
+    uint32_t* ncount; uint32_t* noff; uint32_t* bcount; uint32_t* boff; uint32_t* ucount; uint32_t* rcnt;
+    uint2* bfill;            // running {all, known} counts while bucketizing
+    uint4* rec; uint2* tgt; int2* red; int32_t* ndp; uint32_t* bnode; uint32_t* path; uint32_t* pre;
     int32_t* eos_cost; uint32_t* tcount; uint32_t* toff32;
     uint64_t* tok_off;       // [S+1] output (rebased by tok_base)
     kp_token* tokens;        // output
@@ -46,7 +56,7 @@ int kp_launch_prep_count(const kp_chunk& c, cudaStream_t st);
 int kp_launch_prep_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
 int kp_launch_lattice_count(const kp_chunk& c, const kp_ddict& d, bool count_work, cudaStream_t st);
 int kp_launch_lattice_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
-int kp_launch_bucketize(const kp_chunk& c, cudaStream_t st);
+int kp_launch_bucketize(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
 int kp_launch_viterbi(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
 int kp_launch_pair_count(const kp_chunk& c, cudaStream_t st);
 int kp_launch_backtrace_count(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);

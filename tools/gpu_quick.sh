@@ -3,7 +3,7 @@
 TAG=${1:-q}
 OUT=gpurun_out
 mkdir -p $OUT
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee $OUT/pytest_gpu_$TAG.log
+timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee $OUT/pytest_gpu_$TAG.log
 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu 2>&1 | tail -1 | tee $OUT/bench_$TAG.json
 python - <<PY
 import json

@@ -15,6 +15,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkanpyo_b200.so")
+# tuning experiments: KP_VARIANT=name KP_DEFINES="-DKP_X=1 ..." python -m kanpyo_b200.build builds
+# kanpyo_b200/_variants/libkanpyo_b200.<name>.so; KANPYO_B200_LIB=<path> makes _lib.load() use it.
+VARIANT_DIR = os.path.join(HERE, "_variants")
 SOURCES = ["kp_dict.cu", "kp_kernels.cu", "kp_api.cu", "kp_dictbuild.cpp"]
 HEADERS = ["kp_common.cuh", "kp_kernels.cuh", os.path.join("..", "..", "include", "kanpyo_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -36,6 +39,17 @@ def stale() -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name: str, defines) -> str:
+    os.makedirs(VARIANT_DIR, exist_ok=True)
+    out = os.path.join(VARIANT_DIR, "libkanpyo_b200.%s.so" % name)
+    srcs = [os.path.join(CSRC, f) for f in SOURCES]
+    r = subprocess.run([nvcc()] + NVCC_FLAGS + list(defines) + ["-o", out] + srcs, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building variant %s" % name)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
@@ -55,4 +69,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    if os.environ.get("KP_VARIANT"):
+        print(build_variant(os.environ["KP_VARIANT"], os.environ.get("KP_DEFINES", "").split()))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True))

@@ -47,7 +47,20 @@ struct kp_chunk {
     uint64_t* scan_tmp;      // tile partials for the scans
     uint64_t* totals;        // [8] device scalars: 0 chars, 1 nodes, 2 bucket entries, 3 tokens, 4 P, 5 P_ok, 6 E
     uint32_t* err;           // [2] device flags: 0 utf8, 1 offsets
+    uint32_t* lenhist;       // [kp_len_bins()] counting-sort bins of sentence lengths
+    uint32_t* order;         // [S] sentences sorted by length, longest first (Viterbi work order)
 };
+uint32_t kp_len_bins();
+
+// Hot rows of the connection matrix (see kp_kernels.cu): K rows of `stride` bytes packed in `rows`.
+struct kp_hot {
+    uint32_t K, stride;      // stride: row bytes rounded up to 16
+    uint32_t* hist;          // [conn_col] left-id histogram of a node sample
+    uint8_t* map;            // [conn_col] left id -> hot row or 0xFF
+    uint32_t* ids;           // [K] hot row -> left id
+    int16_t* rows;           // [K * stride / 2]
+};
+uint32_t kp_viterbi_smem_fixed(uint32_t n_left);   // shared memory of kp_viterbi besides the hot rows
 
 uint32_t kp_scan_tmp_elems(uint32_t n);   // uint64 elements of scan_tmp needed for an n-element scan
 
@@ -57,7 +70,9 @@ int kp_launch_prep_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
 int kp_launch_lattice_count(const kp_chunk& c, const kp_ddict& d, bool count_work, cudaStream_t st);
 int kp_launch_lattice_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
 int kp_launch_bucketize(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
-int kp_launch_viterbi(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
+int kp_launch_length_order(const kp_chunk& c, cudaStream_t st);
+int kp_launch_hot_rows(const kp_chunk& c, const kp_ddict& d, const kp_hot& h, cudaStream_t st);
+int kp_launch_viterbi(const kp_chunk& c, const kp_ddict& d, const kp_hot& h, cudaStream_t st);
 int kp_launch_pair_count(const kp_chunk& c, cudaStream_t st);
 int kp_launch_backtrace_count(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
 int kp_launch_fill_pre(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);

@@ -26,9 +26,7 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
-import tempfile
 import threading
 import time
 
@@ -64,57 +62,61 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clocks / throttle reasons DURING the timed region: NVML polled every ~5 ms from a thread (the
+    timed region is tens of milliseconds, too short for `nvidia-smi -lms`); same fields as the
+    B200_PROFILING.md recipe."""
 
     def __init__(self, gpus):
-        self.gpus = set(gpus)
-        self.path = tempfile.mktemp(prefix="kp_clocks_", suffix=".csv")
-        self.proc = None
+        self.gpus = list(gpus)
+        self.samples = []          # (sm_mhz, reasons bitmask) per poll per gpu
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._th = None
 
     def start(self):
         try:
-            self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            self.handles = [nv.nvmlDeviceGetHandleByIndex(i) for i in self.gpus]
+            self.max_mhz = max(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM) for h in self.handles)
         except Exception:
-            self.proc = None
+            self.nv = None
+            return
+
+        def poll():
+            nv = self.nv
+            while not self._stop.is_set():
+                for h in self.handles:
+                    try:
+                        self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                             nv.nvmlDeviceGetCurrentClocksEventReasons(h)))
+                    except Exception:
+                        pass
+                time.sleep(0.004)
+
+        self._th = threading.Thread(target=poll, daemon=True)
+        self._th.start()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        if self._th is None:
             return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.f.close()
-        sm, mx, reasons = [], [], set()
-        try:
-            for line in open(self.path):
-                c = [x.strip() for x in line.split(",")]
-                if len(c) < 9 or not c[0].isdigit() or int(c[0]) not in self.gpus:
-                    continue
-                try:
-                    sm.append(float(c[1]))
-                    mx.append(float(c[2]))
-                except ValueError:
-                    continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            # "under load": the upper half of the samples (idle gaps between steps clock down)
-            sm.sort()
-            out.update(sm_mhz=statistics.median(sm[len(sm) // 2:]), sm_max_mhz=max(mx), samples=len(sm))
-        out["reasons"] = sorted(reasons)
+        self._stop.set()
+        self._th.join(timeout=2)
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        if self.samples:
+            sm = sorted(x[0] for x in self.samples)
+            # "under load": the upper half of the samples (the GPU idles between steps while the host flushes L2)
+            out.update(sm_mhz=float(statistics.median(sm[len(sm) // 2:])), samples=len(sm))
+            bits = 0
+            for _, r in self.samples:
+                bits |= int(r)
+            out["reasons"] = sorted(k for k, v in names.items() if bits & v)
         return out
 
 
@@ -255,6 +257,8 @@ def product_arm(args):
     if world > 1:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         blob = d.pack() if rank == 0 else None
+        warm = torch.zeros(1, device=dev)
+        dist.all_reduce(warm)              # NCCL communicator setup is not part of the broadcast
         barrier()
         e0.record()
         blob_t = sharded.broadcast_dict_blob(blob, 0, dev)
@@ -362,6 +366,13 @@ def product_arm(args):
         vit_launch_ms = stages["viterbi_ms"] / K
         achieved = a_vit / (vit_launch_ms * 1e-3) / 1e9
         kern_ms = sum(stages.values()) / K
+        traffic, traffic_src = None, None
+        try:   # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                tj = json.load(f)["kp_viterbi"]
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": world_bytes * K / (dev_total_ms * 1e-3), "unit": "bytes/s",
             "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": dev_total_ms / K,
@@ -381,7 +392,7 @@ def product_arm(args):
                     "api": "kp_tokenize_batch (C ABI) on pinned host buffers, wall clock around the call"},
             "gpu_launches": int(world_launches),
             "roofline": {"bound": "hbm", "kernel": "kp_viterbi", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": a_vit, "launch_ms": vit_launch_ms,
                          "share_of_kernel_time": vit_launch_ms / kern_ms,
                          "whole_path": {"algorithmic_bytes": a_total, "bytes_per_input_byte": a_total / ctr["bytes"],
@@ -408,7 +419,7 @@ def product_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))

@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(PREP_THREADS) kp_prep_count(const uint8_t* __r
         return;
     }
     uint32_t lo = (uint32_t)lo64, hi = (uint32_t)hi64;
-    uint32_t cnt = 0;
+    uint32_t cnt = 0, conts = 0, claimed = 0;
     bool bad = false;
     for (uint32_t i = lo + lane_id(); i < hi; i += 32) {
         uint32_t c = text[i];
@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(PREP_THREADS) kp_prep_count(const uint8_t* __r
             if (L == 0 || i + L > hi) {
                 bad = true;
             } else if (L > 1) {
+                claimed += L - 1;
                 uint32_t c1 = text[i + 1];
                 uint32_t lo1 = 0x80u, hi1 = 0xBFu;
                 if (c == 0xE0u) lo1 = 0xA0u;
@@ -252,18 +253,12 @@ __global__ void __launch_bounds__(PREP_THREADS) kp_prep_count(const uint8_t* __r
                     if (!is_cont(text[i + k])) bad = true;
             }
         } else {
-            // a continuation byte must be claimed by a lead byte at distance d < its length
-            bool ok = false;
-            for (uint32_t d = 1; d <= 3 && i >= lo + d; d++) {
-                uint32_t p = text[i - d];
-                if (!is_cont(p)) {
-                    ok = lead_len(p) > d;
-                    break;
-                }
-            }
-            if (!ok) bad = true;
+            conts++;
         }
     }
+    // every lead byte verified the continuation bytes it claims, and claims cannot overlap; the
+    // sentence has no stray continuation byte iff their number equals the number claimed
+    if (__reduce_add_sync(KP_FULL, conts) != __reduce_add_sync(KP_FULL, claimed)) bad = true;
     cnt = __reduce_add_sync(KP_FULL, cnt);
     if (__any_sync(KP_FULL, bad) && lane_id() == 0) atomicOr(&err[0], 1u);
     if (lane_id() == 0) nchar[s] = cnt;
@@ -913,7 +908,6 @@ __global__ void __launch_bounds__(BT_THREADS) kp_backtrace_find(uint32_t S, cons
                                                                 const uint32_t* __restrict__ noff,
                                                                 const uint32_t* __restrict__ boff,
                                                                 const uint4* __restrict__ rec,
-                                                                const uint2* __restrict__ tgt,
                                                                 const int32_t* __restrict__ ndp,
                                                                 const uint32_t* __restrict__ bnode,
                                                                 const int16_t* __restrict__ conn, uint32_t conn_row,
@@ -926,42 +920,46 @@ __global__ void __launch_bounds__(BT_THREADS) kp_backtrace_find(uint32_t S, cons
     const uint32_t bb = coff[s] + s, n = coff[s + 1] - coff[s];
     uint32_t cur = noff[bb + n];                 // `self.nodes.len() - 1`: the EOS node
     uint32_t cnt = 0;
+    int dp = ndp[cur];
+    uint4 r = rec[cur];                          // {id|class, start boundary, left|right<<16, cost|len<<16}
     while (true) {
-        const int dp = ndp[cur];
         if (dp >= KP_INF) break;                 // pre_nodes[pos] is None: no total < INF was ever seen
-        const uint2 tg = tgt[cur];
-        const uint32_t b = rec[cur].y;
-        const uint32_t q0 = boff[b], q1 = boff[b + 1];
-        const char* crow = (const char*)conn + (size_t)(tg.x & 0xFFFFu) * conn_row * 2;   // connection.rs:12-14
-        const int want = dp - (int)(int16_t)(tg.x >> 16);
-        uint32_t found = KP_NONE, next = KP_NONE;
+        const uint32_t q0 = boff[r.y], q1 = boff[r.y + 1];
+        const char* crow = (const char*)conn + (size_t)(r.z & 0xFFFFu) * conn_row * 2;   // connection.rs:12-14
+        const int want = dp - (int)(int16_t)(r.w & 0xFFFFu);
+        bool found = false;
+        uint32_t next = KP_NONE;
         for (uint32_t j0 = q0; j0 < q1; j0 += BT_GROUP) {
             const uint32_t j = j0 + l;
             bool ok = false;
             uint32_t nd = KP_NONE;
+            int dpj = 0;                         // BOS: dp None -> 0, morph (0,0,0)
+            uint4 rn = make_uint4(0, 0, 0, 0);
             if (j < q1) {
                 nd = bnode[j];
-                int dpj = 0;
-                uint32_t right = 0;              // BOS: dp None -> 0, morph (0,0,0)
                 if (nd != KP_NONE) {
                     dpj = ndp[nd];
-                    right = rec[nd].z >> 16;
+                    rn = rec[nd];
                 }
-                ok = dpj + ld_conn(crow + right * 2u) == want;
+                ok = dpj + ld_conn(crow + (rn.z >> 16) * 2u) == want;
             }
             const uint32_t m = (__ballot_sync(gmask, ok) >> gshift) & ((1u << BT_GROUP) - 1u);
-            if (m) {                             // first match in list order
-                const uint32_t w = (uint32_t)__ffs(m) - 1;
-                found = j0 + w;
-                next = __shfl_sync(gmask, nd, gshift + w);
+            if (m) {                             // first match in list order; its lane already holds the
+                const uint32_t src = gshift + (uint32_t)__ffs(m) - 1;   // next node's record and dp
+                next = __shfl_sync(gmask, nd, src);
+                dp = __shfl_sync(gmask, dpj, src);
+                r.y = __shfl_sync(gmask, rn.y, src);
+                r.z = __shfl_sync(gmask, rn.z, src);
+                r.w = __shfl_sync(gmask, rn.w, src);
+                found = true;
                 break;
             }
         }
-        if (found == KP_NONE) break;             // unreachable for a consistent dp table
+        if (!found) break;                       // unreachable for a consistent dp table
         if (l == 0) path[bb + cnt] = cur;        // path length <= n + 1 = boundaries of the sentence
         cnt++;
+        if (next == KP_NONE) break;              // reached BOS, which has no predecessor and is not emitted
         cur = next;
-        if (cur == KP_NONE) break;               // reached BOS, which has no predecessor and is not emitted
     }
     if (l == 0) tcount[s] = cnt;
 }
@@ -997,7 +995,7 @@ __global__ void __launch_bounds__(BT_THREADS) kp_backtrace_emit(uint32_t S, cons
 
 int kp_launch_backtrace_count(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
     if (c.S == 0) return 0;
-    kp_backtrace_find<<<(uint32_t)(((uint64_t)c.S * BT_GROUP + BT_THREADS - 1) / BT_THREADS), BT_THREADS, 0, st>>>(c.S, c.coff, c.noff, c.boff, c.rec, c.tgt, c.ndp, c.bnode,
+    kp_backtrace_find<<<(uint32_t)(((uint64_t)c.S * BT_GROUP + BT_THREADS - 1) / BT_THREADS), BT_THREADS, 0, st>>>(c.S, c.coff, c.noff, c.boff, c.rec, c.ndp, c.bnode,
                                                          d.conn, d.conn_row, c.path, c.tcount);
     return kp_launch_check("kp_backtrace_find");
 }

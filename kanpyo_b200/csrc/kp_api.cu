@@ -181,6 +181,7 @@ int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_token
     c.rcnt = t->rcnt.as<uint32_t>();
 
     KP_LAUNCH(kp_launch_prep_fill(c, d, st));
+    KP_LAUNCH(kp_launch_length_order(c, st));        // work order of the Viterbi sweep (needs only coff)
     KP_CUDA(cudaEventRecord(t->ev[EV_PREP], st));
     KP_LAUNCH(kp_launch_lattice_count(c, d, t->count_work, st));
     KP_LAUNCH(kp_launch_scan2(c.ncount, c.bcount, c.noff, c.boff, c.NB, c.scan_tmp, &c.totals[1], &c.totals[2], st));
@@ -216,7 +217,6 @@ int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_token
     KP_CUDA(cudaMemsetAsync(c.bfill, 0, sizeof(uint2) * (NB + 1), st));
     KP_LAUNCH(kp_launch_bucketize(c, d, st));
     KP_CUDA(cudaEventRecord(t->ev[EV_BUCKET], st));
-    KP_LAUNCH(kp_launch_length_order(c, st));
     KP_LAUNCH(kp_launch_hot_rows(c, d, t->hot, st));
     KP_LAUNCH(kp_launch_viterbi(c, d, t->hot, st));
     if (t->count_work) KP_LAUNCH(kp_launch_pair_count(c, st));

@@ -201,7 +201,8 @@ def test_long_unknown_runs(gpu_tok, oracle_tok):
 
 def test_invalid_utf8_rejected(gpu_tok):
     import kanpyo_b200
-    for bad in [b"\xff", b"\xe3\x81", b"a\x80b", b"\xc0\xaf", b"\xed\xa0\x80", b"\xf4\x90\x80\x80", b"\xe3\x81\x82\xe3"]:
+    for bad in [b"\xff", b"\xe3\x81", b"a\x80b", b"\xc0\xaf", b"\xed\xa0\x80", b"\xf4\x90\x80\x80", b"\xe3\x81\x82\xe3",
+                b"\x80", b"\xe3\x81\x82\x80", b"\xf0\x9f\x98", b"\xe0\x9f\xbf", b"\xf0\x8f\xbf\xbf", b"ab\xc2", b"\xbf\xe3\x81\x82"]:
         with pytest.raises(kanpyo_b200.KanpyoB200Error) as e:
             gpu_tok.tokenize_batch_bytes(bad, np.array([0, len(bad)], np.uint64))
         assert e.value.status == -4
@@ -209,6 +210,31 @@ def test_invalid_utf8_rejected(gpu_tok):
     b = "あ".encode("utf-8")
     with pytest.raises(kanpyo_b200.KanpyoB200Error):
         gpu_tok.tokenize_batch_bytes(b, np.array([0, 1, 3], np.uint64))
+
+
+def test_utf8_validation_matches_python(gpu_tok):
+    """The ABI's validity decision equals Python's strict UTF-8 decoder on random byte strings."""
+    import kanpyo_b200
+    rng = np.random.default_rng(11)
+    pool = [b"a", b"\xe3\x81\x82", b"\xc3\xa9", b"\xf0\x9f\x98\x80", b"\x80", b"\xe3", b"\xf0\x9f", b"\xc0", b"\xed\xa0\x80",
+            b"\xef\xbf\xbf", b"\xf4\x8f\xbf\xbf", b"\xf4\x90\x80\x80", b"\xe0\xa0\x80", b"\xe0\x9f\x80", b" "]
+    n_bad = 0
+    for _ in range(400):
+        b = b"".join(pool[k] for k in rng.integers(0, len(pool), rng.integers(1, 8)))
+        try:
+            b.decode("utf-8")
+            valid = True
+        except UnicodeDecodeError:
+            valid = False
+        try:
+            gpu_tok.tokenize_batch_bytes(b, np.array([0, len(b)], np.uint64))
+            accepted = True
+        except kanpyo_b200.KanpyoB200Error as e:
+            assert e.status == -4
+            accepted = False
+        assert accepted == valid, b
+        n_bad += not valid
+    assert 50 < n_bad < 390
 
 
 def test_device_resident_batch(gpu_tok, oracle_tok, vocab):
@@ -244,3 +270,23 @@ def test_idempotent_and_sharding_invariant(gpu_tok, vocab):
     last = a.tok_off[1:].astype(np.int64) - 1
     assert (t["cls"][last] == 0).all()
     assert np.array_equal(t["position"][last].astype(np.uint64), np.diff(off))
+
+
+def test_sharded_tokenizer_single_rank(gpu_ipadic, oracle_tok, vocab):
+    """kanpyo_b200.sharded on one rank over NCCL: dictionary blob round trip through the broadcast
+    path (device blob -> kp_dict_create_from_device_blob) and the gather's world-size-1 path."""
+    import torch
+    import torch.distributed as dist
+    from kanpyo_b200 import corpus, sharded
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda:0"))
+    try:
+        st = sharded.ShardedTokenizer(gpu_ipadic, device=0)
+        text, off = corpus.synth_corpus(vocab, 512, "cfg3")
+        res = st.tokenize_global(text, off)
+        o_off, o_tok, o_cost, _ = oracle_tok.tokenize_batch(text, off)
+        assert_batch_equal(res, o_off, o_tok, o_cost)
+    finally:
+        dist.destroy_process_group()

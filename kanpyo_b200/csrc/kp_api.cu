@@ -84,8 +84,6 @@ struct kp_tokenizer {
     cudaEvent_t ev[EV_COUNT] = {};
     uint64_t chunk_bytes = 64ull << 20;
     bool count_work = false;
-    kp_hot hot = {};
-    DevBuf hot_hist, hot_map, hot_ids, hot_rows;
     // chunk scratch
     DevBuf text, off, nchar, coff, binfo, ncount, noff, bcount, boff, ucount, rcnt, bfill, rec, tgt, red, ndp, bnode, path, pre, lenhist, order,
         tcount, toff32, scan_tmp, totals, err;
@@ -217,8 +215,7 @@ int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_token
     KP_CUDA(cudaMemsetAsync(c.bfill, 0, sizeof(uint2) * (NB + 1), st));
     KP_LAUNCH(kp_launch_bucketize(c, d, st));
     KP_CUDA(cudaEventRecord(t->ev[EV_BUCKET], st));
-    KP_LAUNCH(kp_launch_hot_rows(c, d, t->hot, st));
-    KP_LAUNCH(kp_launch_viterbi(c, d, t->hot, st));
+    KP_LAUNCH(kp_launch_viterbi(c, d, st));
     if (t->count_work) KP_LAUNCH(kp_launch_pair_count(c, st));
     KP_CUDA(cudaEventRecord(t->ev[EV_VITERBI], st));
     KP_LAUNCH(kp_launch_backtrace_count(c, d, st));
@@ -277,29 +274,6 @@ extern "C" int kp_tokenizer_create(const kp_dict* d, kp_tokenizer** out) {
         delete t;
         return KP_ERR_CUDA;
     }
-    // hot rows of the connection matrix: as many as fit in one CTA's shared memory
-    {
-        int optin = 48 * 1024;
-        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d->device);
-        const kp_ddict& v = d->view;
-        const uint32_t stride = (v.conn_row * 2 + 15u) & ~15u;
-        const int64_t avail = (int64_t)optin - kp_viterbi_smem_fixed(v.conn_col) - 1024;
-        int64_t K = avail > 0 ? avail / stride : 0;
-        if (K > v.conn_col) K = v.conn_col;
-        if (K > 255) K = 255;
-        t->hot.K = (uint32_t)K;
-        t->hot.stride = stride;
-        int rc = KP_OK;
-        if ((rc = t->hot_hist.ensure(sizeof(uint32_t) * (v.conn_col + 1))) || (rc = t->hot_map.ensure(v.conn_col + 16)) ||
-            (rc = t->hot_ids.ensure(sizeof(uint32_t) * (K + 1))) || (rc = t->hot_rows.ensure((size_t)K * stride + 16))) {
-            kp_tokenizer_destroy(t);
-            return rc;
-        }
-        t->hot.hist = t->hot_hist.as<uint32_t>();
-        t->hot.map = t->hot_map.as<uint8_t>();
-        t->hot.ids = t->hot_ids.as<uint32_t>();
-        t->hot.rows = t->hot_rows.as<int16_t>();
-    }
     *out = t;
     return KP_OK;
 }
@@ -310,8 +284,7 @@ extern "C" void kp_tokenizer_destroy(kp_tokenizer* t) {
     if (t->stream) cudaStreamSynchronize(t->stream);
     DevBuf* bufs[] = {&t->text, &t->off, &t->nchar, &t->coff, &t->binfo, &t->ncount, &t->noff, &t->bcount, &t->boff,
                       &t->bfill, &t->ucount, &t->rcnt, &t->rec, &t->tgt, &t->red, &t->ndp, &t->bnode, &t->path, &t->pre, &t->lenhist, &t->order, &t->tcount, &t->toff32,
-                      &t->scan_tmp, &t->totals, &t->err, &t->d_tok_off, &t->d_tokens, &t->d_eos, &t->hot_hist, &t->hot_map,
-                      &t->hot_ids, &t->hot_rows};
+                      &t->scan_tmp, &t->totals, &t->err, &t->d_tok_off, &t->d_tokens, &t->d_eos};
     for (DevBuf* b : bufs) b->release();
     PinBuf* pins[] = {&t->h_totals, &t->h_tok_off, &t->h_tokens, &t->h_eos, &t->h_misc};
     for (PinBuf* b : pins) b->release();

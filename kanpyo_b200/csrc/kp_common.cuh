@@ -33,6 +33,8 @@ struct kp_ddict {
     uint32_t n_morphs;
     const int16_t* conn;       // data[row*left_of_target + right_of_previous]
     uint32_t conn_row, conn_col;
+    const int16_t* connT;      // transposed copy: connT[right_of_previous * connT_stride + left_of_target]
+    uint32_t connT_stride;     // elements per row (conn_col rounded up to 64)
     const uint8_t* cat;        // code point -> class
     uint32_t n_cat;
     const kp_catinfo* catinfo; // [256]
@@ -49,7 +51,7 @@ struct kp_blob_header {
     uint64_t total_size;
     uint64_t da_len, n_morphs, conn_row, conn_col, n_cat, n_unk_morphs;
     uint64_t off_da, off_dup, off_morphs, off_conn, off_cat, off_catinfo, off_unk_morphs;
-    uint64_t reserved[4];
+    uint64_t reserved[4];      // [0] offset of the transposed matrix, [1] its row stride in elements
 };
 
 struct kp_dict {

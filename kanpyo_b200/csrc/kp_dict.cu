@@ -159,6 +159,16 @@ static int kp_pack(const kp_dict_arrays* a, std::string* blob) {
     h.off_cat = o;         o = align256(o + a->n_char_category);
     h.off_catinfo = o;     o = align256(o + 256 * sizeof(kp_catinfo));
     h.off_unk_morphs = o;  o = align256(o + (a->n_unk_morphs ? a->n_unk_morphs : 1) * 8);
+    // transposed copy for the Viterbi sweep: row = right_id of the predecessor, column = left_id of the
+    // target, rows padded to whole 128-byte lines (see kp_viterbi)
+    const uint64_t strideT = (a->conn_col + 63) & ~uint64_t(63);
+    if (a->conn_row * strideT * 2 >= (1ull << 31)) {
+        kp_set_error("connection matrix %llu x %llu too large for 31-bit row offsets", (unsigned long long)a->conn_row,
+                     (unsigned long long)a->conn_col);
+        return KP_ERR_DICT;
+    }
+    h.reserved[0] = o;     o = align256(o + a->conn_row * strideT * 2);
+    h.reserved[1] = strideT;
     h.total_size = o;
     blob->assign((size_t)o, '\0');
     char* p = &(*blob)[0];
@@ -176,6 +186,12 @@ static int kp_pack(const kp_dict_arrays* a, std::string* blob) {
     };
     pack_morphs(p + h.off_morphs, a->morphs, a->n_morphs);
     memcpy(p + h.off_conn, a->conn, a->conn_row * a->conn_col * 2);
+    {
+        int16_t* t = (int16_t*)(p + h.reserved[0]);
+        for (uint64_t left = 0; left < a->conn_col; left++)
+            for (uint64_t right = 0; right < a->conn_row; right++)
+                t[right * strideT + left] = a->conn[left * a->conn_row + right];   // get(right, left), connection.rs:12-14
+    }
     memcpy(p + h.off_cat, a->char_category, a->n_char_category);
     memcpy(p + h.off_catinfo, ci.data(), 256 * sizeof(kp_catinfo));
     pack_morphs(p + h.off_unk_morphs, a->unk_morphs, a->n_unk_morphs);
@@ -189,7 +205,7 @@ static int kp_check_header(const kp_blob_header* h, uint64_t size) {
         return KP_ERR_BLOB;
     }
     const uint64_t offs[] = {h->off_da, h->off_dup, h->off_morphs, h->off_conn, h->off_cat, h->off_catinfo,
-                             h->off_unk_morphs};
+                             h->off_unk_morphs, h->reserved[0]};
     for (uint64_t o : offs)
         if (o >= size || (o & 255)) {
             kp_set_error("dictionary blob: bad section offset");
@@ -208,6 +224,8 @@ int kp_view_from_blob(const kp_blob_header* h, const void* d_blob, kp_ddict* v) 
     v->conn = (const int16_t*)(p + h->off_conn);
     v->conn_row = (uint32_t)h->conn_row;
     v->conn_col = (uint32_t)h->conn_col;
+    v->connT = (const int16_t*)(p + h->reserved[0]);
+    v->connT_stride = (uint32_t)h->reserved[1];
     v->cat = (const uint8_t*)(p + h->off_cat);
     v->n_cat = (uint32_t)h->n_cat;
     v->catinfo = (const kp_catinfo*)(p + h->off_catinfo);

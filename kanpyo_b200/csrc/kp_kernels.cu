@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(SENT_THREADS) kp_bucketize(uint32_t S, const u
                 const uint32_t cat = binfo[r.y].w & 0xFFu;  // class of the node's first char = of all its chars
                 slot = base + (bcount[e] - ucount[e]) + ((r.x & KP_ID_MASK) - (uint32_t)d.catinfo[cat].unk_first);
             }
-            red[slot] = make_int2(KP_INF, (int)((r.z >> 16) * 2u));   // right_id as a byte offset into a conn row
+            red[slot] = make_int2(KP_INF, (int)((r.z >> 16) * (d.connT_stride * 2u)));   // byte offset of row right_id in connT
             tgt[i] = make_uint2((r.z & 0xFFFFu) | (r.w << 16), slot);
         }
         __syncwarp();
@@ -536,24 +536,10 @@ int kp_launch_bucketize(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
 }
 
 // =================================================================================================
-// Viterbi forward sweep (lattice.rs:116-143, dp values only).
-//
-// A warp carries 4 sentences, 8 lanes each, and steps all of them boundary by boundary with
-// warp-uniform loop bounds, so the four groups share every issued instruction.  Lanes hold the nodes
-// STARTING at the boundary (targets); each lane folds the boundary's reduced bucket (predecessors)
-// with one DPX add-min per pair:   best = min(best, dp[j] + conn(right_j, left_i))   connection.rs:12-14
-//   dp[i] = min(best + cost_i, INF), kept only if < INF                              lattice.rs:127-139
-// Out-of-range predecessor slots are clamped to the bucket's last entry: a duplicate never changes a
-// minimum.  The argmin (pre_nodes) is NOT tracked here: the back-trace recomputes it for the ~30
-// nodes per sentence that lie on the best path (first j attaining dp[i], which is what the strict '<'
-// update of lattice.rs:136 selects).  dp goes to ndp[i] and is min-merged into the node's reduced
-// slot; the __syncwarp orders those stores before the next boundary's loads.
+// Viterbi work order
 // =================================================================================================
-#ifndef KP_VIT_HOT
-#define KP_VIT_HOT 0         // 1: serve the hottest connection-matrix rows from shared memory (measured slower: DESIGN.md)
-#endif
 constexpr int VIT_GROUP = 8;
-constexpr int VIT_THREADS = KP_VIT_HOT ? 1024 : 128;
+constexpr int VIT_THREADS = 128;
 constexpr uint32_t LEN_BINS = 4096;
 
 // Sentences sorted by length, longest first (counting sort on min(chars, LEN_BINS-1)): the four
@@ -614,77 +600,11 @@ int kp_launch_length_order(const kp_chunk& c, cudaStream_t st) {
     return rc < 0 ? rc : 3;
 }
 
-// =================================================================================================
-// Hot rows of the connection matrix.  ncu shows the sweep's busiest unit is the L1TEX wavefront
-// pipe: the 2-byte gather conn[left][right] costs one wavefront per distinct 128-B line, about one
-// lane per cycle per SM.  Shared memory serves 32 lanes per cycle, but the matrix (3.46 MB for
-// IPADIC) does not fit; the rows (left ids) actually used are heavily skewed though (64 rows cover
-// ~91 % of the lookups on the synthetic corpora), so each call ranks the left ids of a node sample,
-// packs the top K rows into one 16-B aligned block, and every Viterbi CTA pulls that block into
-// shared memory with cp.async.bulk (TMA).  Lookups in the other rows go to global memory.
-// =================================================================================================
-constexpr uint32_t HOT_SAMPLE = 1u << 16;
-
-__global__ void __launch_bounds__(256) kp_left_hist(uint32_t n, uint32_t stride, const uint2* __restrict__ tgt,
-                                                    uint32_t* __restrict__ hist) {
-    uint32_t i = blockIdx.x * 256 + threadIdx.x;
-    uint32_t left = i < n ? (tgt[(size_t)i * stride].x & 0xFFFFu) : 0xFFFFFFFFu;
-    uint32_t m = __match_any_sync(KP_FULL, left);
-    if (i < n && lane_id() == (uint32_t)__ffs(m) - 1) atomicAdd(&hist[left], (uint32_t)__popc(m));
-}
-
-// rank every left id by (count desc, id asc); the first K become hot rows 0..K-1
-__global__ void __launch_bounds__(128) kp_hot_select(const uint32_t* __restrict__ hist, uint32_t n_left, uint32_t K,
-                                                     uint8_t* __restrict__ hot_map, uint32_t* __restrict__ hot_ids) {
-    const uint32_t id = blockIdx.x * 128 + threadIdx.x;
-    if (id >= n_left) return;
-    const uint32_t c = hist[id];
-    uint32_t rank = 0;
-    for (uint32_t o = 0; o < n_left; o++) {
-        const uint32_t co = hist[o];
-        rank += (co > c) || (co == c && o < id);
-    }
-    if (rank < K) {
-        hot_map[id] = (uint8_t)rank;
-        hot_ids[rank] = id;
-    } else {
-        hot_map[id] = 0xFFu;
-    }
-}
-
-__global__ void __launch_bounds__(256) kp_hot_build(const int16_t* __restrict__ conn, uint32_t conn_row,
-                                                    const uint32_t* __restrict__ hot_ids, uint32_t stride_elems,
-                                                    int16_t* __restrict__ hotrows) {
-    const uint32_t id = hot_ids[blockIdx.x];
-    for (uint32_t c = threadIdx.x; c < stride_elems; c += 256)
-        hotrows[(size_t)blockIdx.x * stride_elems + c] = c < conn_row ? conn[(size_t)id * conn_row + c] : (int16_t)0;
-}
-
-int kp_launch_hot_rows(const kp_chunk& c, const kp_ddict& d, const kp_hot& h, cudaStream_t st) {
-    if (!KP_VIT_HOT || h.K == 0) return 0;
-    const uint32_t sample = c.N < HOT_SAMPLE ? c.N : HOT_SAMPLE, stride = sample ? c.N / sample : 1;
-    cudaMemsetAsync(h.hist, 0, sizeof(uint32_t) * d.conn_col, st);
-    if (sample) kp_left_hist<<<(sample + 255) / 256, 256, 0, st>>>(sample, stride, c.tgt, h.hist);
-    kp_hot_select<<<(d.conn_col + 127) / 128, 128, 0, st>>>(h.hist, d.conn_col, h.K, h.map, h.ids);
-    kp_hot_build<<<h.K, 256, 0, st>>>(d.conn, d.conn_row, h.ids, h.stride / 2, h.rows);
-    int rc = kp_launch_check("kp_hot_rows");
-    return rc < 0 ? rc : (sample ? 3 : 2);
-}
-
 __device__ __forceinline__ int ld_conn(const char* p) {
     int v;
     asm("ld.global.nc.s16 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
-// generic address: the shared window for a hot row, global memory otherwise
-__device__ __forceinline__ int ld_conn_generic(const char* p) {
-    int v;
-    asm volatile("ld.s16 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-uint32_t kp_viterbi_smem_fixed(uint32_t n_left) { return ((n_left + 15u) & ~15u) + 16u; }
 
 // =================================================================================================
 // Viterbi forward sweep (lattice.rs:116-143, dp values only).
@@ -700,44 +620,10 @@ uint32_t kp_viterbi_smem_fixed(uint32_t n_left) { return ((n_left + 15u) & ~15u)
 // nodes per sentence that lie on the best path.  dp goes to ndp[i] and is min-merged into the node's
 // reduced slot; the __syncwarp orders those stores before the next boundary's loads.
 // =================================================================================================
-__global__ void __launch_bounds__(VIT_THREADS, KP_VIT_HOT ? 1 : 12) kp_viterbi(
+__global__ void __launch_bounds__(VIT_THREADS, 12) kp_viterbi(
     uint32_t S, const uint32_t* __restrict__ order, const uint32_t* __restrict__ coff, const uint32_t* __restrict__ noff,
     const uint32_t* __restrict__ boff, const uint32_t* __restrict__ rcnt, const uint2* __restrict__ tgt, int2* red,
-    int32_t* __restrict__ ndp, int32_t* __restrict__ eos_cost, const int16_t* __restrict__ conn, uint32_t conn_row,
-    kp_hot hot, uint32_t n_left) {
-#if KP_VIT_HOT
-    extern __shared__ __align__(128) unsigned char vsm[];
-    // layout: [hot rows: K*stride][hot map: n_left bytes, padded][mbarrier]
-    const uint32_t hot_bytes = hot.K * hot.stride;
-    uint8_t* smap = vsm + hot_bytes;
-    if (hot.K) {
-        uint64_t* mbar = (uint64_t*)(smap + ((n_left + 15u) & ~15u));
-        const uint32_t mb = smem_u32(mbar);
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(hot_bytes) : "memory");
-            for (uint32_t o = 0; o < hot_bytes; o += 32768) {           // TMA bulk copies, <= 32 KB each
-                const uint32_t sz = hot_bytes - o < 32768 ? hot_bytes - o : 32768;
-                asm volatile(
-                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                        smem_u32(vsm + o)),
-                    "l"((const char*)hot.rows + o), "r"(sz), "r"(mb)
-                    : "memory");
-            }
-        }
-        for (uint32_t i = threadIdx.x; i < n_left; i += VIT_THREADS) smap[i] = hot.map[i];
-        __syncthreads();
-        uint32_t done = 0;
-        while (!done) {
-            asm volatile(
-                "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                : "=r"(done)
-                : "r"(mb)
-                : "memory");
-        }
-    }
-#endif
+    int32_t* __restrict__ ndp, int32_t* __restrict__ eos_cost, const int16_t* __restrict__ connT) {
     const uint32_t slot = (blockIdx.x * VIT_THREADS + threadIdx.x) / VIT_GROUP;
     const uint32_t l = threadIdx.x & (VIT_GROUP - 1);
     const bool has = slot < S;
@@ -755,18 +641,13 @@ __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_HOT ? 1 : 12) kp_viterbi(
         rbn = boff[bb];
         rn = rcnt[bb];
     }
-    const size_t row_bytes = (size_t)conn_row * 2;
-    // row pointer of a target: generic address into the shared hot block, or the global matrix
-    auto row_of = [&](uint32_t left) -> const char* {
-#if KP_VIT_HOT
-        const uint32_t hi = hot.K ? smap[left] : 0xFFu;
-        if (hi != 0xFFu) return (const char*)vsm + hi * hot.stride;
-#endif
-        return (const char*)conn + left * row_bytes;
-    };
+    // connT[right_j][left_i] (connection.rs:12-14, transposed): the lanes of a group share the row of
+    // predecessor j and differ in the column, and the left ids of the nodes starting at one boundary
+    // cluster (noun / unknown-word ids are neighbours), so a group's gather touches ~2 lines, not ~5
+    auto col_of = [&](uint32_t left) -> const char* { return (const char*)connT + left * 2u; };
     uint2 tgn = make_uint2(0u, KP_NONE);          // first target chunk of the next boundary, prefetched
     if (has && t0 + l < t1n) tgn = tgt[t0 + l];
-    const char* crown = row_of(tgn.x & 0xFFFFu);
+    const char* crown = col_of(tgn.x & 0xFFFFu);
     for (uint32_t p = 0; p < steps; p++) {
         const bool act = has && p <= n;
         const uint32_t t1 = act ? t1n : t0, rb = rbn, R = act ? rn : 0u;
@@ -784,18 +665,14 @@ __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_HOT ? 1 : 12) kp_viterbi(
             const char* crow = crown;
             if (tc) {
                 tg = tv ? tgt[t0 + tc + l] : make_uint2(0u, KP_NONE);
-                crow = row_of(tg.x & 0xFFFFu);
+                crow = col_of(tg.x & 0xFFFFu);
             }
             int best = INT_MAX;
             for (uint32_t jj = 0; jj < Rmax; jj += 4) {
 #pragma unroll
                 for (uint32_t u = 0; u < 4; u++) {
                     const int2 e = red[min(qb + jj + u, qlast)];
-#if KP_VIT_HOT
-                    best = __viaddmin_s32(e.x, ld_conn_generic(crow + (uint32_t)e.y), best);
-#else
                     best = __viaddmin_s32(e.x, ld_conn(crow + (uint32_t)e.y), best);
-#endif
                 }
             }
             if (tv) {
@@ -808,30 +685,17 @@ __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_HOT ? 1 : 12) kp_viterbi(
         }
         // the next boundary's first targets: the address does not depend on this step's results
         tgn = (has && p < n && t1 + l < t1n) ? tgt[t1 + l] : make_uint2(0u, KP_NONE);
-        crown = row_of(tgn.x & 0xFFFFu);
+        crown = col_of(tgn.x & 0xFFFFu);
         __syncwarp();
         t0 = t1;
     }
 }
 
-int kp_launch_viterbi(const kp_chunk& c, const kp_ddict& d, const kp_hot& h, cudaStream_t st) {
+int kp_launch_viterbi(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
     if (c.S == 0) return 0;
-    uint32_t smem = 0;
-#if KP_VIT_HOT
-    smem = h.K * h.stride + kp_viterbi_smem_fixed(d.conn_col);
-    static thread_local uint32_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(kp_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            kp_set_error("kp_viterbi: %u bytes of shared memory refused: %s", smem, cudaGetErrorString(e));
-            return KP_ERR_CUDA;
-        }
-        configured = smem;
-    }
-#endif
     uint32_t blocks = (uint32_t)(((uint64_t)c.S * VIT_GROUP + VIT_THREADS - 1) / VIT_THREADS);
-    kp_viterbi<<<blocks, VIT_THREADS, smem, st>>>(c.S, c.order, c.coff, c.noff, c.boff, c.rcnt, c.tgt, c.red, c.ndp,
-                                                  c.eos_cost, d.conn, d.conn_row, h, d.conn_col);
+    kp_viterbi<<<blocks, VIT_THREADS, 0, st>>>(c.S, c.order, c.coff, c.noff, c.boff, c.rcnt, c.tgt, c.red, c.ndp,
+                                               c.eos_cost, d.connT);
     return kp_launch_check("kp_viterbi");
 }
 

@@ -12,7 +12,8 @@
 //   ucount  u32[NB]       UNKNOWN nodes ending at each boundary (subset of bcount)
 //   bnode   u32[N]        the reference's `edges` lists: per bucket entry (ascending node index) the node
 //                         index (KP_NONE for BOS); bucket of boundary b = [boff[b], boff[b+1])
-//   red     int2[N]       REDUCED buckets, what the Viterbi sweep scans as predecessors: {min dp, right_id*2}.
+//   red     int2[N]       REDUCED buckets, what the Viterbi sweep scans as predecessors: {min dp, byte offset of
+//                         row right_id in the transposed connection matrix}.
 //                         Region of boundary b = [boff[b], boff[b] + rcnt[b]): one entry per known node
 //                         ending at b (BOS first at a sentence's first boundary), then one entry per
 //                         unknown-morph id of the class of the char before b, shared by ALL unknown nodes
@@ -52,16 +53,6 @@ struct kp_chunk {
 };
 uint32_t kp_len_bins();
 
-// Hot rows of the connection matrix (see kp_kernels.cu): K rows of `stride` bytes packed in `rows`.
-struct kp_hot {
-    uint32_t K, stride;      // stride: row bytes rounded up to 16
-    uint32_t* hist;          // [conn_col] left-id histogram of a node sample
-    uint8_t* map;            // [conn_col] left id -> hot row or 0xFF
-    uint32_t* ids;           // [K] hot row -> left id
-    int16_t* rows;           // [K * stride / 2]
-};
-uint32_t kp_viterbi_smem_fixed(uint32_t n_left);   // shared memory of kp_viterbi besides the hot rows
-
 uint32_t kp_scan_tmp_elems(uint32_t n);   // uint64 elements of scan_tmp needed for an n-element scan
 
 // each returns the number of kernels launched (negative kp_status on launch failure)
@@ -71,8 +62,7 @@ int kp_launch_lattice_count(const kp_chunk& c, const kp_ddict& d, bool count_wor
 int kp_launch_lattice_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
 int kp_launch_bucketize(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
 int kp_launch_length_order(const kp_chunk& c, cudaStream_t st);
-int kp_launch_hot_rows(const kp_chunk& c, const kp_ddict& d, const kp_hot& h, cudaStream_t st);
-int kp_launch_viterbi(const kp_chunk& c, const kp_ddict& d, const kp_hot& h, cudaStream_t st);
+int kp_launch_viterbi(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
 int kp_launch_pair_count(const kp_chunk& c, cudaStream_t st);
 int kp_launch_backtrace_count(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
 int kp_launch_fill_pre(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);

@@ -36,7 +36,7 @@ IPADIC_TARBALL = os.path.join(os.path.dirname(_HERE), "third_party", "mecab-ipad
                               "mecab-ipadic-2.7.0-20070801.tar.gz")
 IPADIC_SHA256 = "b62f527d881c504576baed9c6ef6561554658b175ce6ae0096a60307e49e3523"
 CACHE_DIR = os.path.join(_HERE, "_cache")
-CACHE_VERSION = 2
+CACHE_VERSION = 3
 
 
 class BuilderError(ValueError):

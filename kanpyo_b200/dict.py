@@ -110,9 +110,21 @@ class Dict:
         kw_off = np.zeros(len(self.keywords) + 1, np.uint64)
         if self.keywords:
             kw_off[1:] = np.cumsum([len(k) for k in self.keywords], dtype=np.uint64)
+        extra = {}
+        for tag, table in (("f", self.features), ("u", self.unk_features)):
+            if table:
+                rows, names = table
+                off = np.zeros(len(rows) + 1, np.uint64)
+                if rows:
+                    off[1:] = np.cumsum([len(r) for r in rows], dtype=np.uint64)
+                extra[tag + "_off"] = off
+                extra[tag + "_flat"] = np.fromiter((v for r in rows for v in r), np.uint32, int(off[-1]))
+                blob = "\x00".join(names).encode("utf-8")          # feature strings never contain NUL
+                extra[tag + "_names"] = np.frombuffer(blob, np.uint8)
         np.savez(path, **{k: getattr(self, k) for k in self._NPZ},
                  conn_shape=np.array([self.conn_row, self.conn_col], np.uint64),
-                 char_class=np.array(self.char_class if self.char_class else [""]), kw_blob=kw_blob, kw_off=kw_off)
+                 char_class=np.array(self.char_class if self.char_class else [""]), kw_blob=kw_blob, kw_off=kw_off,
+                 **extra)
 
     @classmethod
     def load_npz(cls, path: str) -> "Dict":
@@ -120,5 +132,24 @@ class Dict:
         kw_blob = z["kw_blob"].tobytes()
         kw_off = z["kw_off"]
         keywords = [kw_blob[int(kw_off[i]):int(kw_off[i + 1])] for i in range(len(kw_off) - 1)]
+
+        def table(tag):
+            if tag + "_off" not in z:
+                return ()
+            off, flat = z[tag + "_off"], z[tag + "_flat"]
+            rows = [flat[int(off[i]):int(off[i + 1])].tolist() for i in range(len(off) - 1)]
+            return rows, z[tag + "_names"].tobytes().decode("utf-8").split("\x00")
+
         return cls(**{k: z[k] for k in cls._NPZ}, conn_row=int(z["conn_shape"][0]), conn_col=int(z["conn_shape"][1]),
-                   char_class=[str(x) for x in z["char_class"]], keywords=keywords)
+                   char_class=[str(x) for x in z["char_class"]], keywords=keywords, features=table("f"),
+                   unk_features=table("u"))
+
+    # ---- feature strings (src/bin/kanpyo.rs:174-197; not read by the hot path) ---------------------
+    def token_features(self, token) -> list:
+        """`morph_feature_table.morph_features[id-1]` mapped through `name_list` for a Known token, the
+        unknown dictionary's table for an Unknown one, [] for EOS."""
+        cls, tid = int(token.cls), int(token.id)
+        if tid == 0 or cls == 0:
+            return []
+        rows, names = self.features if cls == 1 else self.unk_features
+        return [names[i] for i in rows[tid - 1]]

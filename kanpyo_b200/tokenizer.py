@@ -107,6 +107,11 @@ class Tokenizer:
             out.append(Token(int(t["id"]), cls, pos, start, start + int(t["char_len"]), surface))
         return out
 
+    def format_tokens(self, tokens) -> str:
+        """The `kanpyo tokenize` output, `print_tokens` of src/bin/kanpyo.rs:174-197: one line per token,
+        `surface<TAB>feature,feature,...`."""
+        return "".join("%s\t%s\n" % (t.surface, ",".join(self.dict.token_features(t))) for t in tokens)
+
     # ---- packed batch entry points -----------------------------------------------------------------
     def tokenize_batch_bytes(self, text, offsets: np.ndarray) -> BatchResult:
         """Host text (bytes / uint8 array) + uint64 offsets [n+1] -> BatchResult (kp_tokenize_batch)."""

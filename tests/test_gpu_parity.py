@@ -115,6 +115,13 @@ def test_golden_sentences(gpu_tok):
         assert [[t.id, int(t.cls), t.position, t.start, t.end, t.surface] for t in toks] == [t[:6] for t in s["tokens"]]
 
 
+def test_readme_cli_output(gpu_tok):                      # README.md:73-107 through print_tokens' format
+    from test_oracle_pins import README
+    for text, expect in README.items():
+        out = gpu_tok.format_tokens(gpu_tok.tokenize(text))
+        assert out == "".join("%s\t%s\n" % (s, f) for s, f in expect)
+
+
 def test_lattice_node_parity(gpu_tok, oracle_tok):
     """Lattice{nodes} order + dp/pre of every node (lattice.rs:101-154), including dead nodes."""
     for s in ["すもももももももものうち", "Tシャツを3枚買ったABC", "\U0001F600の犬", "", "カタカナカタカナ", "あ" * 40,

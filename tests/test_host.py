@@ -261,3 +261,20 @@ def test_sharded_gather_gloo_world2(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, "rank %d failed:\n%s" % (r, o)
         assert "worker %d ok" % r in o
+
+
+def test_product_feature_tables_match_goldens():
+    """print_tokens' feature join (src/bin/kanpyo.rs:174-197) from the PRODUCT builder's tables, checked
+    on the ids of the committed golden tokens (no compute involved)."""
+    import json
+    from types import SimpleNamespace
+    from kanpyo_b200 import builder
+    d = builder.ipadic()
+    with open(os.path.join(ROOT, "tests", "golden", "ipadic_sentences.json"), encoding="utf-8") as f:
+        golden = json.load(f)
+    n = 0
+    for sent in golden["sentences"]:
+        for tid, cls, _pos, _start, _end, _surface, feats in sent["tokens"]:
+            assert ",".join(d.token_features(SimpleNamespace(id=tid, cls=cls))) == feats
+            n += 1
+    assert n > 100

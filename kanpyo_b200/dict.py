@@ -101,6 +101,18 @@ class Dict:
         except Exception:
             pass
 
+    # ---- the reference's `.dict` zip container (kanpyo-dict/src/dict.rs:51-116) ---------------------
+    def build(self, f):
+        """`Dict::build(&self, f)`: write the six-member zip the reference's tools read."""
+        from . import dictfile
+        dictfile.save_dict(self, f)
+
+    @classmethod
+    def load(cls, f) -> "Dict":
+        """`Dict::load(r)`: read a dictionary written by the reference's `ipa-dict-builder` (or by build())."""
+        from . import dictfile
+        return dictfile.load_dict(f)
+
     # ---- persistence of the flat form (a cache, not the reference's .dict zip) -------------------
     _NPZ = ("da", "dup_ids", "dup_counts", "morphs", "conn", "char_category", "invoke_list", "group_list", "unk_cat",
             "unk_first_id", "unk_count", "unk_morphs")

@@ -278,3 +278,51 @@ def test_product_feature_tables_match_goldens():
             assert ",".join(d.token_features(SimpleNamespace(id=tid, cls=cls))) == feats
             n += 1
     assert n > 100
+
+
+def test_dict_container_round_trip_and_known_bytes(tmp_path, oracle_mod):
+    """The reference's `.dict` zip container (dict.rs:51-116): hand-derived byte vectors for the fixed
+    little-endian sections and the bincode-standard sections, then full round trips."""
+    import io
+    import struct
+    import zipfile
+    from kanpyo_b200 import builder, dictfile
+    # bincode config::standard(): varint lengths, u8 / bool one byte each
+    assert dictfile.encode_chardef(["A"], [0, 1], [1], [0]) == bytes([1, 1, 0x41, 2, 0, 1, 1, 1, 1, 0])
+    big = dictfile.encode_chardef([], np.zeros(65536, np.uint8), [], [])
+    assert big[:6] == bytes([0, 252]) + struct.pack("<I", 65536) and len(big) == 6 + 65536 + 2
+    assert dictfile.encode_feature_table(([[1, 300]], ["", "x"])) == bytes([1, 2, 1, 251, 0x2C, 0x01, 2, 0, 1, 0x78])
+    d = to_product_dict(reference_fixture_dict(oracle_mod))
+    d.features = ([[1, 2], [1, 2], [1, 3]], ["", "名詞", "一般", "固有"])
+    d.unk_features = ([[1], [1]], ["", "未知"])
+    buf = io.BytesIO()
+    dictfile.save_dict(d, buf)
+    with zipfile.ZipFile(io.BytesIO(buf.getvalue())) as z:
+        assert sorted(z.namelist()) == sorted(dictfile.MEMBERS)
+        m = z.read("morph.dict")                                         # morph.rs:61-71
+        assert m == struct.pack("<q", 3) + struct.pack("<9h", 0, 0, 1000, 1, 1, 1200, 2, 2, 1100)
+        c = z.read("connection.dict")                                    # connection.rs:43-50
+        assert c == struct.pack("<QQ", 3, 3) + struct.pack("<9h", 0, 100, 200, 100, 0, 100, 200, 100, 0)
+        ix = z.read("index.dict")                                        # da.rs:236-245, index.rs:74-83
+        n = struct.unpack_from("<Q", ix)[0]
+        assert n == len(d.da) and ix[8 + 8 * n:] == struct.pack("<Q", 0)
+        u = z.read("unk.dict")                                           # unk_dict.rs:62-72
+        assert u[:8 + 2 * 17] == struct.pack("<Q", 2) + struct.pack("<BqQ", 1, 1, 1) + struct.pack("<BqQ", 2, 2, 1)
+    e = dictfile.load_dict(buf.getvalue())
+    for k in Dict_FIELDS:
+        assert np.array_equal(getattr(e, k), getattr(d, k)), k
+    assert (e.conn_row, e.conn_col, e.char_class) == (3, 3, d.char_class)
+    assert e.features == d.features and e.unk_features == d.unk_features
+    # IPADIC: file -> Dict -> identical packed device blob
+    full = builder.ipadic()
+    path = tmp_path / "ipa.dict"
+    dictfile.save_dict(full, str(path))
+    back = dictfile.load_dict(str(path))
+    assert np.array_equal(back.pack(), full.pack())
+    assert back.features == full.features and back.unk_features == full.unk_features
+    with pytest.raises(dictfile.DictFormatError):
+        dictfile.load_dict(b"not a zip")
+
+
+Dict_FIELDS = ("da", "dup_ids", "dup_counts", "morphs", "conn", "char_category", "invoke_list", "group_list", "unk_cat",
+               "unk_first_id", "unk_count", "unk_morphs")

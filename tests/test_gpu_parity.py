@@ -122,6 +122,25 @@ def test_readme_cli_output(gpu_tok):                      # README.md:73-107 thr
         assert out == "".join("%s\t%s\n" % (s, f) for s, f in expect)
 
 
+def test_graphviz_dump(gpu_tok):                          # src/graphviz.rs:30-163 over kp_lattice_dump
+    from kanpyo_b200.graphviz import graphviz
+    text = "すもももももももものうち"
+    dot = graphviz(gpu_tok, text)
+    lines = dot.splitlines()
+    assert lines[0] == "graph lattice {" and lines[1] == "dpi=48;" and lines[-1] == "}"
+    assert any(ln.startswith('0 [label="BOS", shape=ellipse, color=blue, peripheries=2]') for ln in lines)
+    assert any(ln.startswith('1 [label="EOS", shape=ellipse, color=blue, peripheries=2]') for ln in lines)
+    bold = [ln for ln in lines if "style=bold" in ln]
+    assert len(bold) == len(gpu_tok.tokenize(text))            # BOS->t1, t1->t2, ..., t7->EOS
+    assert not any("shape=diamond" in ln for ln in lines)      # off-path unknown nodes are hidden
+    assert 'label="すもも\n名詞/一般/すもも/スモモ/スモモ\n' in dot
+    full = graphviz(gpu_tok, text, dpi=96, full_state=True)
+    n_nodes = len(gpu_tok.lattice(text))
+    assert full.splitlines()[1] == "dpi=96;"
+    assert sum(1 for ln in full.splitlines() if " [label=" in ln and " -- " not in ln) == n_nodes
+    assert "shape=diamond" in full
+
+
 def test_lattice_node_parity(gpu_tok, oracle_tok):
     """Lattice{nodes} order + dp/pre of every node (lattice.rs:101-154), including dead nodes."""
     for s in ["すもももももももものうち", "Tシャツを3枚買ったABC", "\U0001F600の犬", "", "カタカナカタカナ", "あ" * 40,

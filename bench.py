@@ -348,12 +348,14 @@ def product_arm(args):
     # ---- reduce over ranks: bytes summed, times max ------------------------------------------------
     vals = torch.tensor([sum(dev_ms), sum(e2e_s) * 1e3, wall_s * 1e3, stages["viterbi_ms"], stages["lattice_ms"],
                          gather_ms or 0.0], dtype=torch.float64, device=dev)
-    sums = torch.tensor([n_bytes, n_tokens, launches], dtype=torch.float64, device=dev)
+    h2d_b = int(h_text.numel() + 8 * h_off.numel())
+    d2h_b = int(16 * n_tokens + 8 * (S + 1) + 4 * S)
+    sums = torch.tensor([n_bytes, n_tokens, launches, h2d_b, d2h_b], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     dev_total_ms, e2e_total_ms, wall_ms, vit_ms, lat_ms, gather_max = vals.tolist()
-    world_bytes, world_tokens, world_launches = sums.tolist()
+    world_bytes, world_tokens, world_launches, world_h2d, world_d2h = sums.tolist()
 
     if rank == 0:
         K = args.steps
@@ -386,8 +388,7 @@ def product_arm(args):
                                  "max over ranks; wall_ms_per_step includes the L2 flushes"},
             "wall_ms_per_step": wall_ms / K,
             "e2e": {"value": world_bytes * K / (e2e_total_ms * 1e-3), "unit": "bytes/s",
-                    "h2d_bytes_per_step": int(h_text.numel() + 8 * h_off.numel()),
-                    "d2h_bytes_per_step": int(16 * n_tokens + 8 * (S + 1) + 4 * S),
+                    "h2d_bytes_per_step": int(world_h2d), "d2h_bytes_per_step": int(world_d2h),
                     "ms_per_step": e2e_total_ms / K,
                     "api": "kp_tokenize_batch (C ABI) on pinned host buffers, wall clock around the call"},
             "gpu_launches": int(world_launches),

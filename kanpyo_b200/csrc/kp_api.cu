@@ -85,7 +85,7 @@ struct kp_tokenizer {
     uint64_t chunk_bytes = 64ull << 20;
     bool count_work = false;
     // chunk scratch
-    DevBuf text, off, nchar, coff, binfo, ncount, noff, bcount, boff, ucount, rcnt, bfill, rec, tgt, red, ndp, bnode, path, pre, lenhist, order,
+    DevBuf text, off, nchar, coff, binfo, ncount, noff, bcount, boff, ucount, rcnt, nhit, hits, bfill, rec, tgt, red, ndp, bnode, path, pre, lenhist, order,
         tcount, toff32, scan_tmp, totals, err;
     // device outputs
     DevBuf d_tok_off, d_tokens, d_eos;
@@ -166,6 +166,8 @@ int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_token
     KP_TRY(t->boff.ensure(sizeof(uint32_t) * (NB + 2)));
     KP_TRY(t->bfill.ensure(sizeof(uint2) * (NB + 1)));
     KP_TRY(t->ucount.ensure(sizeof(uint32_t) * (NB + 1)));
+    KP_TRY(t->nhit.ensure(NB + 16));
+    KP_TRY(t->hits.ensure(sizeof(uint4) * 2 * (NB + 1)));
     KP_TRY(t->rcnt.ensure(sizeof(uint32_t) * (NB + 1)));
     KP_TRY(t->scan_tmp.ensure(sizeof(uint64_t) * kp_scan_tmp_elems((uint32_t)NB + 1)));
     c.scan_tmp = t->scan_tmp.as<uint64_t>();
@@ -176,6 +178,8 @@ int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_token
     c.boff = t->boff.as<uint32_t>();
     c.bfill = t->bfill.as<uint2>();
     c.ucount = t->ucount.as<uint32_t>();
+    c.nhit = t->nhit.as<uint8_t>();
+    c.hits = t->hits.as<uint4>();
     c.rcnt = t->rcnt.as<uint32_t>();
 
     KP_LAUNCH(kp_launch_prep_fill(c, d, st));
@@ -283,7 +287,7 @@ extern "C" void kp_tokenizer_destroy(kp_tokenizer* t) {
     cudaSetDevice(t->device);
     if (t->stream) cudaStreamSynchronize(t->stream);
     DevBuf* bufs[] = {&t->text, &t->off, &t->nchar, &t->coff, &t->binfo, &t->ncount, &t->noff, &t->bcount, &t->boff,
-                      &t->bfill, &t->ucount, &t->rcnt, &t->rec, &t->tgt, &t->red, &t->ndp, &t->bnode, &t->path, &t->pre, &t->lenhist, &t->order, &t->tcount, &t->toff32,
+                      &t->bfill, &t->ucount, &t->rcnt, &t->nhit, &t->hits, &t->rec, &t->tgt, &t->red, &t->ndp, &t->bnode, &t->path, &t->pre, &t->lenhist, &t->order, &t->tcount, &t->toff32,
                       &t->scan_tmp, &t->totals, &t->err, &t->d_tok_off, &t->d_tokens, &t->d_eos};
     for (DevBuf* b : bufs) b->release();
     PinBuf* pins[] = {&t->h_totals, &t->h_tok_off, &t->h_tokens, &t->h_eos, &t->h_misc};

@@ -58,12 +58,21 @@ __global__ void __launch_bounds__(SCAN_THREADS) kp_scan_tile_sums(const uint32_t
     __shared__ uint64_t sh[SCAN_THREADS / 32];
     uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     uint64_t sa = 0, sb = 0;
+    if (base + SCAN_ITEMS <= n) {                 // 32 contiguous, 32-byte aligned bytes per thread
+        const uint4 a0 = *(const uint4*)(a + base), a1 = *(const uint4*)(a + base + 4);
+        sa = (uint64_t)a0.x + a0.y + a0.z + a0.w + a1.x + a1.y + a1.z + a1.w;
+        if (TWO) {
+            const uint4 b0 = *(const uint4*)(b + base), b1 = *(const uint4*)(b + base + 4);
+            sb = (uint64_t)b0.x + b0.y + b0.z + b0.w + b1.x + b1.y + b1.z + b1.w;
+        }
+    } else {
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        uint32_t i = base + k;
-        if (i < n) {
-            sa += a[i];
-            if (TWO) sb += b[i];
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            uint32_t i = base + k;
+            if (i < n) {
+                sa += a[i];
+                if (TWO) sb += b[i];
+            }
         }
     }
     uint64_t ra = block_reduce_u64(sa, sh);
@@ -136,15 +145,24 @@ __global__ void __launch_bounds__(SCAN_THREADS) kp_scan_apply(const uint32_t* __
     uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     uint32_t va[SCAN_ITEMS], vb[SCAN_ITEMS];
     uint32_t sa = 0, sb = 0;
+    const bool full = base + SCAN_ITEMS <= n;     // 32 contiguous, 32-byte aligned bytes per thread
+    if (full) {
+        *(uint4*)&va[0] = *(const uint4*)(a + base);
+        *(uint4*)&va[4] = *(const uint4*)(a + base + 4);
+        if (TWO) {
+            *(uint4*)&vb[0] = *(const uint4*)(b + base);
+            *(uint4*)&vb[4] = *(const uint4*)(b + base + 4);
+        }
+    }
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         uint32_t i = base + k;
-        va[k] = i < n ? a[i] : 0;
-        sa += va[k];
-        if (TWO) {
-            vb[k] = i < n ? b[i] : 0;
-            sb += vb[k];
+        if (!full) {
+            va[k] = i < n ? a[i] : 0;
+            if (TWO) vb[k] = i < n ? b[i] : 0;
         }
+        sa += va[k];
+        if (TWO) sb += vb[k];
     }
     uint32_t xa = sa, xb = sb;
     for (int o = 1; o < 32; o <<= 1) {
@@ -167,15 +185,30 @@ __global__ void __launch_bounds__(SCAN_THREADS) kp_scan_apply(const uint32_t* __
     }
     oa += xa - sa;
     ob += xb - sb;
+    uint32_t ra[SCAN_ITEMS], rb[SCAN_ITEMS];
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
-        uint32_t i = base + k;
-        if (i < n) {
-            out_a[i] = oa;
-            oa += va[k];
-            if (TWO) {
-                out_b[i] = ob;
-                ob += vb[k];
+        ra[k] = oa;
+        oa += va[k];
+        if (TWO) {
+            rb[k] = ob;
+            ob += vb[k];
+        }
+    }
+    if (full) {                                   // out_a / out_b have n + 1 elements: base + 8 <= n is in range
+        *(uint4*)(out_a + base) = *(uint4*)&ra[0];
+        *(uint4*)(out_a + base + 4) = *(uint4*)&ra[4];
+        if (TWO) {
+            *(uint4*)(out_b + base) = *(uint4*)&rb[0];
+            *(uint4*)(out_b + base + 4) = *(uint4*)&rb[4];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            uint32_t i = base + k;
+            if (i < n) {
+                out_a[i] = ra[k];
+                if (TWO) out_b[i] = rb[k];
             }
         }
     }
@@ -344,11 +377,14 @@ int kp_launch_prep_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
 // =================================================================================================
 constexpr int LAT_THREADS = 256;
 
+constexpr uint32_t LAT_HITS = 4;   // trie hits per start boundary remembered from the counting walk
+
 template <bool FILL, bool WORK>
 __global__ void __launch_bounds__(LAT_THREADS) kp_lattice_walk(const uint8_t* __restrict__ text,
                                                           const uint4* __restrict__ binfo, uint32_t NB, kp_ddict d,
                                                           uint32_t* __restrict__ ncount, uint32_t* __restrict__ bcount,
-                                                          uint32_t* __restrict__ ucount,
+                                                          uint32_t* __restrict__ ucount, uint8_t* __restrict__ nhit,
+                                                          uint4* __restrict__ hits,
                                                           const uint32_t* __restrict__ noff, uint4* __restrict__ rec,
                                                           uint64_t* __restrict__ totals) {
     uint32_t b = blockIdx.x * LAT_THREADS + threadIdx.x;
@@ -358,13 +394,34 @@ __global__ void __launch_bounds__(LAT_THREADS) kp_lattice_walk(const uint8_t* __
         const uint32_t bp = bi.x, send = bi.y;
         uint32_t o = FILL ? noff[b] : 0;
         uint32_t total = 0;
+        // one Known node per (hit x duplicate) (lattice.rs:177-188, index.rs:46-51)
+        auto expand = [&](uint32_t id, uint32_t nch) {
+            const uint32_t k = (uint32_t)d.dup[id] + 1;
+            for (uint32_t j = 0; j < k; j++) {
+                const short4 m = d.morphs[id + j - 1];                       // lattice.rs:182
+                rec[o++] = make_uint4((id + j) | ((uint32_t)KP_CLASS_KNOWN << KP_KIND_SHIFT), b,
+                                      (uint32_t)(uint16_t)m.x | ((uint32_t)(uint16_t)m.y << 16),
+                                      (uint32_t)(uint16_t)m.z | (nch << 16));
+            }
+        };
         if (bp == send) {
             // EOS: Dummy node with morph (0,0,0) (lattice.rs:165-175)
             if (FILL) rec[o] = make_uint4((uint32_t)KP_CLASS_DUMMY << KP_KIND_SHIFT, b, 0u, 0u);
             total = 1;
         } else {
-            bool matched = false;
-            if (d.da_len > KP_ROOT_ID) {
+            // The counting walk remembers its first LAT_HITS hits {id, chars}; the fill pass replays them
+            // and walks the trie again only for the few boundaries with more hits than that.
+            uint32_t nh = FILL ? nhit[b] : 0;
+            uint4 h01 = make_uint4(0, 0, 0, 0), h23 = make_uint4(0, 0, 0, 0);
+            if (FILL && nh <= LAT_HITS) {
+                if (nh > 0) h01 = hits[2 * (size_t)b];
+                if (nh > 2) h23 = hits[2 * (size_t)b + 1];
+                if (nh > 0) expand(h01.x, h01.y);
+                if (nh > 1) expand(h01.z, h01.w);
+                if (nh > 2) expand(h23.x, h23.y);
+                if (nh > 3) expand(h23.z, h23.w);
+            } else if (d.da_len > KP_ROOT_ID) {
+                nh = 0;
                 int prev = KP_ROOT_ID;
                 int base = d.da[KP_ROOT_ID].x;
                 uint32_t nch = 0;
@@ -382,25 +439,32 @@ __global__ void __launch_bounds__(LAT_THREADS) kp_lattice_walk(const uint8_t* __
                         int2 na = d.da[ahead];
                         if (na.y == q && na.x < 0) {                         // da.rs:167-174
                             uint32_t id = (uint32_t)(-na.x);
-                            uint32_t k = (uint32_t)d.dup[id] + 1;            // index.rs:46-51
-                            matched = true;
                             if (!FILL) {
+                                const uint32_t k = (uint32_t)d.dup[id] + 1;  // index.rs:46-51
                                 total += k;
                                 atomicAdd(&bcount[b + nch], k);
+                                if (nh == 0) { h01.x = id; h01.y = nch; }
+                                else if (nh == 1) { h01.z = id; h01.w = nch; }
+                                else if (nh == 2) { h23.x = id; h23.y = nch; }
+                                else if (nh == 3) { h23.z = id; h23.w = nch; }
                             } else {
-                                for (uint32_t j = 0; j < k; j++) {
-                                    short4 m = d.morphs[id + j - 1];         // lattice.rs:182
-                                    rec[o++] = make_uint4((id + j) | ((uint32_t)KP_CLASS_KNOWN << KP_KIND_SHIFT), b,
-                                                          (uint32_t)(uint16_t)m.x | ((uint32_t)(uint16_t)m.y << 16),
-                                                          (uint32_t)(uint16_t)m.z | (nch << 16));
-                                }
+                                expand(id, nch);
                             }
+                            nh++;
                         }
                     }
                     prev = q;
                     base = nq.x;
                 }
+                if (!FILL) {
+                    nhit[b] = (uint8_t)min(nh, 255u);
+                    if (nh > 0) hits[2 * (size_t)b] = h01;
+                    if (nh > 2) hits[2 * (size_t)b + 1] = h23;
+                }
+            } else if (!FILL) {
+                nhit[b] = 0;
             }
+            const bool matched = nh > 0;
             // unknown words (lattice.rs:42-99)
             const kp_catinfo ci = d.catinfo[bi.w & 0xFFu];
             if ((!matched || (ci.flags & 1u)) && ci.unk_count) {
@@ -436,18 +500,18 @@ int kp_launch_lattice_count(const kp_chunk& c, const kp_ddict& d, bool count_wor
     uint32_t blocks = (c.NB + LAT_THREADS - 1) / LAT_THREADS;
     if (count_work)
         kp_lattice_walk<false, true><<<blocks, LAT_THREADS, 0, st>>>(c.text, c.binfo, c.NB, d, c.ncount, c.bcount, c.ucount,
-                                                                nullptr, nullptr, c.totals);
+                                                                c.nhit, c.hits, nullptr, nullptr, c.totals);
     else
         kp_lattice_walk<false, false><<<blocks, LAT_THREADS, 0, st>>>(c.text, c.binfo, c.NB, d, c.ncount, c.bcount, c.ucount,
-                                                                 nullptr, nullptr, c.totals);
+                                                                 c.nhit, c.hits, nullptr, nullptr, c.totals);
     return kp_launch_check("kp_lattice_walk<count>");
 }
 
 int kp_launch_lattice_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
     if (c.NB == 0) return 0;
     uint32_t blocks = (c.NB + LAT_THREADS - 1) / LAT_THREADS;
-    kp_lattice_walk<true, false><<<blocks, LAT_THREADS, 0, st>>>(c.text, c.binfo, c.NB, d, nullptr, nullptr, nullptr, c.noff,
-                                                            c.rec, c.totals);
+    kp_lattice_walk<true, false><<<blocks, LAT_THREADS, 0, st>>>(c.text, c.binfo, c.NB, d, nullptr, nullptr, nullptr, c.nhit,
+                                                            c.hits, c.noff, c.rec, c.totals);
     return kp_launch_check("kp_lattice_walk<fill>");
 }
 

@@ -9,7 +9,8 @@ def to_product_dict(od):
         da=od.da, dup_ids=od.dup_ids, dup_counts=od.dup_counts, morphs=od.morphs, conn_row=od.conn_row,
         conn_col=od.conn_col, conn=od.conn, char_category=od.char_category, invoke_list=od.invoke_list,
         group_list=od.group_list, unk_cat=od.unk_cat, unk_first_id=od.unk_first_id, unk_count=od.unk_count,
-        unk_morphs=od.unk_morphs, char_class=list(od.char_class), keywords=list(od.keywords))
+        unk_morphs=od.unk_morphs, char_class=list(od.char_class), keywords=list(od.keywords),
+        features=tuple(od.features) if od.features else (), unk_features=tuple(od.unk_features) if od.unk_features else ())
 
 
 def reference_fixture_dict(oracle_mod):

@@ -138,7 +138,10 @@ def test_graphviz_dump(gpu_tok):                          # src/graphviz.rs:30-1
     n_nodes = len(gpu_tok.lattice(text))
     assert full.splitlines()[1] == "dpi=96;"
     assert sum(1 for ln in full.splitlines() if " [label=" in ln and " -- " not in ln) == n_nodes
-    assert "shape=diamond" in full
+    text2 = "Tシャツを3枚買ったABC"                             # unknown nodes on (3, ABC) and off (BC, C) the path
+    hidden, shown = graphviz(gpu_tok, text2), graphviz(gpu_tok, text2, full_state=True)
+    assert "shape=diamond" in shown and "shape=diamond" not in hidden
+    assert 'color=red, peripheries=2]' in hidden               # best-path unknown nodes stay visible
 
 
 def test_lattice_node_parity(gpu_tok, oracle_tok):

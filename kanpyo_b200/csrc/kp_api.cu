@@ -73,6 +73,7 @@ struct PinBuf {   // pinned host memory, preserved on growth
     T* as() const { return (T*)p; }
 };
 
+constexpr uint32_t KP_PERM_REFRESH = 16;
 enum { EV_START, EV_H2D, EV_PREP, EV_LATTICE, EV_BUCKET, EV_VITERBI, EV_BACKTRACE, EV_END, EV_COUNT };
 
 }  // namespace
@@ -84,6 +85,9 @@ struct kp_tokenizer {
     cudaEvent_t ev[EV_COUNT] = {};
     uint64_t chunk_bytes = 64ull << 20;
     bool count_work = false;
+    kp_perm perm = {};
+    uint32_t perm_age = 0;     // passes since the column order was last ranked
+    DevBuf perm_hist, perm_map, perm_conn;
     // chunk scratch
     DevBuf text, off, nchar, coff, binfo, ncount, noff, bcount, boff, ucount, rcnt, nhit, hits, bfill, rec, tgt, red, ndp, bnode, path, pre, lenhist, order,
         tcount, toff32, scan_tmp, totals, err;
@@ -217,9 +221,11 @@ int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_token
     KP_LAUNCH(kp_launch_lattice_fill(c, d, st));
     KP_CUDA(cudaEventRecord(t->ev[EV_LATTICE], st));
     KP_CUDA(cudaMemsetAsync(c.bfill, 0, sizeof(uint2) * (NB + 1), st));
-    KP_LAUNCH(kp_launch_bucketize(c, d, st));
+    if (t->perm_age % KP_PERM_REFRESH == 0) KP_LAUNCH(kp_launch_column_order(c, d, t->perm, st));
+    t->perm_age++;
+    KP_LAUNCH(kp_launch_bucketize(c, d, t->perm, st));
     KP_CUDA(cudaEventRecord(t->ev[EV_BUCKET], st));
-    KP_LAUNCH(kp_launch_viterbi(c, d, st));
+    KP_LAUNCH(kp_launch_viterbi(c, d, t->perm, st));
     if (t->count_work) KP_LAUNCH(kp_launch_pair_count(c, st));
     KP_CUDA(cudaEventRecord(t->ev[EV_VITERBI], st));
     KP_LAUNCH(kp_launch_backtrace_count(c, d, st));
@@ -278,6 +284,20 @@ extern "C" int kp_tokenizer_create(const kp_dict* d, kp_tokenizer** out) {
         delete t;
         return KP_ERR_CUDA;
     }
+    {   // column order of the sweep's connection matrix: a private, permuted copy of the transposed matrix
+        const kp_ddict& v = d->view;
+        int rc = KP_OK;
+        if ((rc = t->perm_hist.ensure(sizeof(uint32_t) * (v.conn_col + 1))) ||
+            (rc = t->perm_map.ensure(sizeof(uint16_t) * (v.conn_col + 1))) ||
+            (rc = t->perm_conn.ensure(sizeof(int16_t) * ((size_t)v.conn_row * v.connT_stride + 8)))) {
+            kp_tokenizer_destroy(t);
+            return rc;
+        }
+        t->perm.hist = t->perm_hist.as<uint32_t>();
+        t->perm.perm = t->perm_map.as<uint16_t>();
+        t->perm.connP = t->perm_conn.as<int16_t>();
+        cudaMemset(t->perm.connP, 0, sizeof(int16_t) * (size_t)v.conn_row * v.connT_stride);   // row padding
+    }
     *out = t;
     return KP_OK;
 }
@@ -288,7 +308,8 @@ extern "C" void kp_tokenizer_destroy(kp_tokenizer* t) {
     if (t->stream) cudaStreamSynchronize(t->stream);
     DevBuf* bufs[] = {&t->text, &t->off, &t->nchar, &t->coff, &t->binfo, &t->ncount, &t->noff, &t->bcount, &t->boff,
                       &t->bfill, &t->ucount, &t->rcnt, &t->nhit, &t->hits, &t->rec, &t->tgt, &t->red, &t->ndp, &t->bnode, &t->path, &t->pre, &t->lenhist, &t->order, &t->tcount, &t->toff32,
-                      &t->scan_tmp, &t->totals, &t->err, &t->d_tok_off, &t->d_tokens, &t->d_eos};
+                      &t->scan_tmp, &t->totals, &t->err, &t->d_tok_off, &t->d_tokens, &t->d_eos, &t->perm_hist, &t->perm_map,
+                      &t->perm_conn};
     for (DevBuf* b : bufs) b->release();
     PinBuf* pins[] = {&t->h_totals, &t->h_tok_off, &t->h_tokens, &t->h_eos, &t->h_misc};
     for (PinBuf* b : pins) b->release();

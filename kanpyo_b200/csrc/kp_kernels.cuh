@@ -20,7 +20,7 @@
 //                         with that id ending at b (they have the same right_id; only their minimum dp
 //                         can matter to a successor)
 //   rcnt    u32[NB]       entries in the reduced bucket of each boundary
-//   tgt     uint2[N]      per node, what the sweep needs of a TARGET: {left | cost<<16, reduced slot}
+//   tgt     uint2[N]      per node, what the sweep needs of a TARGET: {column of left_id | cost<<16, reduced slot}
 //                         (global index into red; KP_NONE for EOS)
 //   ndp     i32[N]        dp of every node (the back-trace and the lattice dump read it)
 //   path    u32[NB]       best path of each sentence, back to front, at the sentence's boundary base
@@ -54,6 +54,13 @@ struct kp_chunk {
 };
 uint32_t kp_len_bins();
 
+// Column order of the Viterbi sweep's connection matrix (see kp_kernels.cu)
+struct kp_perm {
+    uint32_t* hist;          // [conn_col] left-id histogram of a node sample
+    uint16_t* perm;          // [conn_col] left id -> column
+    int16_t* connP;          // [conn_row * connT_stride] transposed matrix with permuted columns
+};
+
 uint32_t kp_scan_tmp_elems(uint32_t n);   // uint64 elements of scan_tmp needed for an n-element scan
 
 // each returns the number of kernels launched (negative kp_status on launch failure)
@@ -61,9 +68,10 @@ int kp_launch_prep_count(const kp_chunk& c, cudaStream_t st);
 int kp_launch_prep_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
 int kp_launch_lattice_count(const kp_chunk& c, const kp_ddict& d, bool count_work, cudaStream_t st);
 int kp_launch_lattice_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
-int kp_launch_bucketize(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
+int kp_launch_column_order(const kp_chunk& c, const kp_ddict& d, const kp_perm& pm, cudaStream_t st);
+int kp_launch_bucketize(const kp_chunk& c, const kp_ddict& d, const kp_perm& pm, cudaStream_t st);
 int kp_launch_length_order(const kp_chunk& c, cudaStream_t st);
-int kp_launch_viterbi(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
+int kp_launch_viterbi(const kp_chunk& c, const kp_ddict& d, const kp_perm& pm, cudaStream_t st);
 int kp_launch_pair_count(const kp_chunk& c, cudaStream_t st);
 int kp_launch_backtrace_count(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
 int kp_launch_fill_pre(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);

@@ -237,7 +237,10 @@ int kp_launch_scan2(const uint32_t* a, const uint32_t* b, uint32_t* oa, uint32_t
 // =================================================================================================
 // Prep: UTF-8 validation + chars per sentence; then per-boundary info.  One warp per sentence.
 // =================================================================================================
-constexpr int PREP_THREADS = 256;
+#ifndef KP_PREP_THREADS
+#define KP_PREP_THREADS 256
+#endif
+constexpr int PREP_THREADS = KP_PREP_THREADS;
 
 __device__ __forceinline__ bool is_cont(uint32_t c) { return (c & 0xC0u) == 0x80u; }
 __device__ __forceinline__ uint32_t lead_len(uint32_t c) {  // 0 = not a valid lead byte
@@ -375,7 +378,10 @@ int kp_launch_prep_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
 // sentence.  Pass 1 counts nodes per start boundary and per end boundary; pass 2 (after the scans)
 // writes the node records in the reference's insertion order.
 // =================================================================================================
-constexpr int LAT_THREADS = 256;
+#ifndef KP_LAT_THREADS
+#define KP_LAT_THREADS 256
+#endif
+constexpr int LAT_THREADS = KP_LAT_THREADS;
 
 constexpr uint32_t LAT_HITS = 4;   // trie hits per start boundary remembered from the counting walk
 
@@ -576,7 +582,10 @@ int kp_launch_column_order(const kp_chunk& c, const kp_ddict& d, const kp_perm& 
 // each and the sweep min-merges into it.  The minimum VALUE is unchanged, and the back-trace picks
 // the first predecessor attaining it from the full list, so results are bit-identical.
 // =================================================================================================
-constexpr int SENT_THREADS = 128;   // 4 sentences per CTA
+#ifndef KP_SENT_THREADS
+#define KP_SENT_THREADS 64
+#endif
+constexpr int SENT_THREADS = KP_SENT_THREADS;   // one warp per sentence
 constexpr uint32_t BK_SMEM = 512;   // boundaries per sentence whose fill cursors fit in shared memory
 
 __global__ void __launch_bounds__(SENT_THREADS) kp_bucketize(uint32_t S, const uint32_t* __restrict__ coff,
@@ -893,7 +902,10 @@ int kp_launch_pair_count(const kp_chunk& c, cudaStream_t st) {
 // pass 2 (after the scan of the path lengths) writes the tokens front to back.
 // =================================================================================================
 constexpr int BT_THREADS = 128;
-constexpr int BT_GROUP = 8;
+#ifndef KP_BT_GROUP
+#define KP_BT_GROUP 8
+#endif
+constexpr int BT_GROUP = KP_BT_GROUP;
 
 __global__ void __launch_bounds__(BT_THREADS) kp_backtrace_find(uint32_t S, const uint32_t* __restrict__ coff,
                                                                 const uint32_t* __restrict__ noff,

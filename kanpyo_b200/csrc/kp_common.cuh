@@ -13,6 +13,11 @@ constexpr int KP_INF = 1 << 30;                // src/lattice.rs:117
 constexpr uint32_t KP_MAX_UNKNOWN_LEN = 1024;  // src/lattice.rs:55
 constexpr uint32_t KP_NONE = 0xFFFFFFFFu;      // Option::None for slot / node indices
 
+// first-character table of the trie walk (kp_dict.cu): code points it covers, and its two markers
+constexpr uint32_t KP_FIRST_CPS = 0x10000u;
+constexpr int KP_FIRST_DEAD = -1;              // a transition fails inside the character: no hits at all
+constexpr int KP_FIRST_SLOW = -2;              // not representable: walk this character from the root
+
 // node.x packs id (30 bits) and class (2 bits)
 constexpr uint32_t KP_ID_MASK = 0x3FFFFFFFu;
 constexpr int KP_KIND_SHIFT = 30;
@@ -35,6 +40,7 @@ struct kp_ddict {
     uint32_t conn_row, conn_col;
     const int16_t* connT;      // transposed copy: connT[right_of_previous * connT_stride + left_of_target]
     uint32_t connT_stride;     // elements per row (conn_col rounded up to 64)
+    const int2* first;         // [KP_FIRST_CPS] trie state after one whole character: {state, base[state]}
     const uint8_t* cat;        // code point -> class
     uint32_t n_cat;
     const kp_catinfo* catinfo; // [256]
@@ -51,7 +57,8 @@ struct kp_blob_header {
     uint64_t total_size;
     uint64_t da_len, n_morphs, conn_row, conn_col, n_cat, n_unk_morphs;
     uint64_t off_da, off_dup, off_morphs, off_conn, off_cat, off_catinfo, off_unk_morphs;
-    uint64_t reserved[4];      // [0] offset of the transposed matrix, [1] its row stride in elements
+    uint64_t reserved[4];      // [0] offset of the transposed matrix, [1] its row stride in elements,
+                               // [2] offset of the first-character table
 };
 
 struct kp_dict {

@@ -169,6 +169,7 @@ static int kp_pack(const kp_dict_arrays* a, std::string* blob) {
     }
     h.reserved[0] = o;     o = align256(o + a->conn_row * strideT * 2);
     h.reserved[1] = strideT;
+    h.reserved[2] = o;     o = align256(o + (uint64_t)KP_FIRST_CPS * 8);   // first-character table (below)
     h.total_size = o;
     blob->assign((size_t)o, '\0');
     char* p = &(*blob)[0];
@@ -192,6 +193,48 @@ static int kp_pack(const kp_dict_arrays* a, std::string* blob) {
             for (uint64_t right = 0; right < a->conn_row; right++)
                 t[right * strideT + left] = a->conn[left * a->conn_row + right];   // get(right, left), connection.rs:12-14
     }
+    {
+        // First-character table: for every code point below 0x10000, the trie state reached from the
+        // root after the bytes of that one character -- {state, base[state]}, or {KP_FIRST_DEAD, 0}
+        // when a transition fails inside the character (then search_common_prefix_of returns
+        // nothing, da.rs:160-164).  The counting walk starts there instead of at the root.  Keys are
+        // whole UTF-8 strings, so no key can end inside a character; a table entry whose skipped
+        // terminator probes (da.rs:165-174) would hit anyway is marked KP_FIRST_SLOW and that
+        // character is walked byte by byte from the root.
+        int32_t* t = (int32_t*)(p + h.reserved[2]);
+        const int32_t* da = a->da;
+        const uint64_t n = a->da_len;
+        for (uint32_t cp = 0; cp < KP_FIRST_CPS; cp++) {
+            int32_t st = KP_FIRST_SLOW, stbase = 0;
+            uint8_t bytes[3];
+            int L = 0;
+            if (cp < 0x80) { bytes[0] = (uint8_t)cp; L = 1; }
+            else if (cp < 0x800) { bytes[0] = (uint8_t)(0xC0 | (cp >> 6)); bytes[1] = (uint8_t)(0x80 | (cp & 0x3F)); L = 2; }
+            else if (cp < 0xD800 || cp >= 0xE000) {
+                bytes[0] = (uint8_t)(0xE0 | (cp >> 12)); bytes[1] = (uint8_t)(0x80 | ((cp >> 6) & 0x3F));
+                bytes[2] = (uint8_t)(0x80 | (cp & 0x3F)); L = 3;
+            }
+            if (L && n > (uint64_t)KP_ROOT_ID) {
+                int64_t prev = KP_ROOT_ID, base = da[2 * KP_ROOT_ID];
+                bool dead = false, slow = false;
+                int64_t q = 0;
+                for (int k = 0; k < L && !dead; k++) {
+                    q = base + bytes[k];
+                    if (q < 0 || (uint64_t)q >= n || da[2 * q + 1] != prev) { dead = true; break; }
+                    const int64_t ahead = da[2 * q];
+                    if (k < L - 1 && ahead >= 0 && (uint64_t)ahead < n && da[2 * ahead + 1] == q && da[2 * ahead] < 0)
+                        slow = true;
+                    prev = q;
+                    base = da[2 * q];
+                }
+                if (slow) { st = KP_FIRST_SLOW; }
+                else if (dead) { st = KP_FIRST_DEAD; }
+                else { st = (int32_t)q; stbase = (int32_t)base; }
+            }
+            t[2 * cp] = st;
+            t[2 * cp + 1] = stbase;
+        }
+    }
     memcpy(p + h.off_cat, a->char_category, a->n_char_category);
     memcpy(p + h.off_catinfo, ci.data(), 256 * sizeof(kp_catinfo));
     pack_morphs(p + h.off_unk_morphs, a->unk_morphs, a->n_unk_morphs);
@@ -205,9 +248,9 @@ static int kp_check_header(const kp_blob_header* h, uint64_t size) {
         return KP_ERR_BLOB;
     }
     const uint64_t offs[] = {h->off_da, h->off_dup, h->off_morphs, h->off_conn, h->off_cat, h->off_catinfo,
-                             h->off_unk_morphs, h->reserved[0]};
+                             h->off_unk_morphs, h->reserved[0], h->reserved[2]};
     for (uint64_t o : offs)
-        if (o >= size || (o & 255)) {
+        if (o == 0 || o >= size || (o & 255)) {
             kp_set_error("dictionary blob: bad section offset");
             return KP_ERR_BLOB;
         }
@@ -226,6 +269,7 @@ int kp_view_from_blob(const kp_blob_header* h, const void* d_blob, kp_ddict* v) 
     v->conn_col = (uint32_t)h->conn_col;
     v->connT = (const int16_t*)(p + h->reserved[0]);
     v->connT_stride = (uint32_t)h->reserved[1];
+    v->first = (const int2*)(p + h->reserved[2]);
     v->cat = (const uint8_t*)(p + h->off_cat);
     v->n_cat = (uint32_t)h->n_cat;
     v->catinfo = (const kp_catinfo*)(p + h->off_catinfo);

@@ -384,9 +384,70 @@ int kp_launch_prep_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
 constexpr int LAT_THREADS = KP_LAT_THREADS;
 
 constexpr uint32_t LAT_HITS = 4;   // trie hits per start boundary remembered from the counting walk
+#ifndef KP_WALK_ILP
+#define KP_WALK_ILP 1
+#endif
+#ifndef KP_FILL_FLAT
+#define KP_FILL_FLAT 1
+#endif
+#ifndef KP_WALK_T1
+#define KP_WALK_T1 1
+#endif
+#ifndef KP_CNT_MINB
+#define KP_CNT_MINB 6
+#endif
+#ifndef KP_FILL_MINB
+#define KP_FILL_MINB 5
+#endif
+
+// A remembered hit is {id, chars | (duplicates << 16)}: the fill pass needs neither the trie nor `dup`.
+// A morph {left, right, cost, 0} read as two words: {left | right << 16, cost}.
+__device__ __forceinline__ uint2 ld_morph(const short4* __restrict__ m, uint32_t i) {
+    return __ldg((const uint2*)m + i);
+}
+__device__ __forceinline__ uint4 kp_node_rec(uint32_t id, uint32_t kind, uint32_t b, uint2 m, uint32_t nch) {
+    return make_uint4(id | (kind << KP_KIND_SHIFT), b, m.x, (m.y & 0xFFFFu) | (nch << 16));
+}
+
+// Fill pass, boundaries with more than LAT_HITS hits (a few percent): walk the trie again and write
+// one Known node per (hit x duplicate) (lattice.rs:177-188, index.rs:46-51).  Kept out of line so its
+// registers do not count against the replay path.  Returns the next free record index.
+struct kp_trie_view {
+    const int2* da;
+    uint32_t da_len;
+    const uint16_t* dup;
+    const short4* morphs;
+};
+__device__ __noinline__ uint32_t kp_fill_rewalk(const uint8_t* __restrict__ text, uint32_t bp, uint32_t send,
+                                                uint32_t b, kp_trie_view d, uint4* __restrict__ rec, uint32_t o) {
+    int prev = KP_ROOT_ID;
+    int base = d.da[KP_ROOT_ID].x;
+    uint32_t nch = 0;
+    for (uint32_t i = bp; i < send; i++) {
+        const uint32_t c = text[i];
+        nch += !is_cont(c);
+        const int q = base + (int)c;                                         // da.rs:160
+        if ((uint32_t)q >= d.da_len) break;                                  // Vec::get -> None (da.rs:161)
+        const int2 nq = d.da[q];
+        if (nq.y != prev) break;                                             // da.rs:162-164
+        const int ahead = nq.x;                                              // + TERMINATOR (0), da.rs:165
+        if ((uint32_t)ahead < d.da_len) {
+            const int2 na = d.da[ahead];
+            if (na.y == q && na.x < 0) {                                     // da.rs:167-174
+                const uint32_t id = (uint32_t)(-na.x);
+                const uint32_t k = (uint32_t)d.dup[id] + 1;                  // index.rs:46-51
+                for (uint32_t j = 0; j < k; j++)
+                    rec[o++] = kp_node_rec(id + j, KP_CLASS_KNOWN, b, ld_morph(d.morphs, id + j - 1), nch);   // lattice.rs:182
+            }
+        }
+        prev = q;
+        base = nq.x;
+    }
+    return o;
+}
 
 template <bool FILL, bool WORK>
-__global__ void __launch_bounds__(LAT_THREADS) kp_lattice_walk(const uint8_t* __restrict__ text,
+__global__ void __launch_bounds__(LAT_THREADS, FILL ? KP_FILL_MINB : KP_CNT_MINB) kp_lattice_walk(const uint8_t* __restrict__ text,
                                                           const uint4* __restrict__ binfo, uint32_t NB, kp_ddict d,
                                                           uint32_t* __restrict__ ncount, uint32_t* __restrict__ bcount,
                                                           uint32_t* __restrict__ ucount, uint8_t* __restrict__ nhit,
@@ -400,14 +461,17 @@ __global__ void __launch_bounds__(LAT_THREADS) kp_lattice_walk(const uint8_t* __
         const uint32_t bp = bi.x, send = bi.y;
         uint32_t o = FILL ? noff[b] : 0;
         uint32_t total = 0;
-        // one Known node per (hit x duplicate) (lattice.rs:177-188, index.rs:46-51)
-        auto expand = [&](uint32_t id, uint32_t nch) {
-            const uint32_t k = (uint32_t)d.dup[id] + 1;
-            for (uint32_t j = 0; j < k; j++) {
-                const short4 m = d.morphs[id + j - 1];                       // lattice.rs:182
-                rec[o++] = make_uint4((id + j) | ((uint32_t)KP_CLASS_KNOWN << KP_KIND_SHIFT), b,
-                                      (uint32_t)(uint16_t)m.x | ((uint32_t)(uint16_t)m.y << 16),
-                                      (uint32_t)(uint16_t)m.z | (nch << 16));
+        // one Known node per (hit x duplicate) (lattice.rs:177-188, index.rs:46-51), with the duplicate
+        // count and the first morph already in registers; the remaining morph loads go out two at a
+        // time ahead of the stores that need them
+        auto expand_known = [&](uint32_t id, uint32_t y, uint2 m0) {
+            const uint32_t nch = y & 0xFFFFu, k = (y >> 16) + 1;
+            rec[o++] = kp_node_rec(id, KP_CLASS_KNOWN, b, m0, nch);
+            for (uint32_t j = 1; j < k; j += 2) {
+                const uint2 ma = ld_morph(d.morphs, id + j - 1);
+                const uint2 mb = ld_morph(d.morphs, id + min(j + 1, k - 1) - 1);
+                rec[o++] = kp_node_rec(id + j, KP_CLASS_KNOWN, b, ma, nch);
+                if (j + 1 < k) rec[o++] = kp_node_rec(id + j + 1, KP_CLASS_KNOWN, b, mb, nch);
             }
         };
         if (bp == send) {
@@ -415,17 +479,108 @@ __global__ void __launch_bounds__(LAT_THREADS) kp_lattice_walk(const uint8_t* __
             if (FILL) rec[o] = make_uint4((uint32_t)KP_CLASS_DUMMY << KP_KIND_SHIFT, b, 0u, 0u);
             total = 1;
         } else {
-            // The counting walk remembers its first LAT_HITS hits {id, chars}; the fill pass replays them
-            // and walks the trie again only for the few boundaries with more hits than that.
+            // The counting walk remembers its first LAT_HITS hits {id, chars | dups << 16}; the fill pass
+            // replays them and walks the trie again only for the few boundaries with more hits than that.
             uint32_t nh = FILL ? nhit[b] : 0;
             uint4 h01 = make_uint4(0, 0, 0, 0), h23 = make_uint4(0, 0, 0, 0);
+            if (FILL && KP_FILL_FLAT) h01 = hits[2 * (size_t)b];   // not waiting for nh (unused when nh == 0)
             if (FILL && nh <= LAT_HITS) {
-                if (nh > 0) h01 = hits[2 * (size_t)b];
-                if (nh > 2) h23 = hits[2 * (size_t)b + 1];
-                if (nh > 0) expand(h01.x, h01.y);
-                if (nh > 1) expand(h01.z, h01.w);
-                if (nh > 2) expand(h23.x, h23.y);
-                if (nh > 3) expand(h23.z, h23.w);
+                if (KP_FILL_FLAT) {
+                    if (nh > 2) h23 = hits[2 * (size_t)b + 1];
+                    // first morph of every hit: four independent gathers in flight together
+                    const uint2 z = make_uint2(0u, 0u);
+                    const uint2 m0 = nh > 0 ? ld_morph(d.morphs, h01.x - 1) : z;
+                    const uint2 m1 = nh > 1 ? ld_morph(d.morphs, h01.z - 1) : z;
+                    const uint2 m2 = nh > 2 ? ld_morph(d.morphs, h23.x - 1) : z;
+                    const uint2 m3 = nh > 3 ? ld_morph(d.morphs, h23.z - 1) : z;
+                    if (nh > 0) expand_known(h01.x, h01.y, m0);
+                    if (nh > 1) expand_known(h01.z, h01.w, m1);
+                    if (nh > 2) expand_known(h23.x, h23.y, m2);
+                    if (nh > 3) expand_known(h23.z, h23.w, m3);
+                } else {
+                    if (nh > 0) h01 = hits[2 * (size_t)b];
+                    if (nh > 2) h23 = hits[2 * (size_t)b + 1];
+                    if (nh > 0) expand_known(h01.x, h01.y, ld_morph(d.morphs, h01.x - 1));
+                    if (nh > 1) expand_known(h01.z, h01.w, ld_morph(d.morphs, h01.z - 1));
+                    if (nh > 2) expand_known(h23.x, h23.y, ld_morph(d.morphs, h23.x - 1));
+                    if (nh > 3) expand_known(h23.z, h23.w, ld_morph(d.morphs, h23.z - 1));
+                }
+            } else if (FILL) {
+                if (d.da_len > KP_ROOT_ID)
+                    o = kp_fill_rewalk(text, bp, send, b, kp_trie_view{d.da, d.da_len, d.dup, d.morphs}, rec, o);
+            } else if (!WORK && KP_WALK_ILP && d.da_len > KP_ROOT_ID) {
+                // Counting walk with the loads of one step issued together: the terminator probe
+                // da[base[q]] and the next transition da[base[q] + next byte] depend only on da[q]
+                // (da.rs:160-174), and the next text byte is fetched a step ahead.  A failed range
+                // test is carried as check = -1, which no state index equals.
+                const int2 dead = make_int2(0, -1);
+                uint32_t i = bp, nch = 0;
+                uint32_t c = text[i];
+                int prev = KP_ROOT_ID, q;
+                int2 nq = dead;
+                int2 f = make_int2(KP_FIRST_SLOW, 0);
+                if (KP_WALK_T1 && c < 0xF0u) {
+                    // the whole first character in one lookup (table built in kp_dict.cu); the text is
+                    // valid UTF-8, so the continuation bytes are inside the sentence
+                    uint32_t cp = c, L = 1;
+                    if (c >= 0xE0u) { cp = ((c & 0x0Fu) << 12) | ((text[i + 1] & 0x3Fu) << 6) | (text[i + 2] & 0x3Fu); L = 3; }
+                    else if (c >= 0x80u) { cp = ((c & 0x1Fu) << 6) | (text[i + 1] & 0x3Fu); L = 2; }
+                    f = d.first[cp];
+                    if (f.x != KP_FIRST_SLOW) {          // arrive in state f.x as if by its last byte
+                        i += L - 1;
+                        nch = 1;
+                        c = 0x80u;                       // counted already
+                        prev = 0;
+                        q = f.x;
+                        nq = f.x >= 0 ? make_int2(f.y, 0) : dead;
+                    }
+                }
+                if (f.x == KP_FIRST_SLOW) {
+                    q = d.da[KP_ROOT_ID].x + (int)c;                         // da.rs:160
+                    nq = (uint32_t)q < d.da_len ? d.da[q] : dead;            // Vec::get -> None (da.rs:161)
+                }
+                uint32_t c1 = i + 1 < send ? text[i + 1] : 0u;
+                while (nq.y == prev) {                                       // da.rs:162-164
+                    nch += !is_cont(c);
+                    const int ahead = nq.x;                                  // + TERMINATOR (0), da.rs:165
+                    const int q2 = nq.x + (int)c1;
+                    const uint32_t i2 = i + 1;
+                    const int2 na = (uint32_t)ahead < d.da_len ? d.da[ahead] : dead;
+                    const int2 nq2 = (i2 < send && (uint32_t)q2 < d.da_len) ? d.da[q2] : dead;
+                    const uint32_t c2 = i2 + 1 < send ? text[i2 + 1] : 0u;
+                    if (na.y == q && na.x < 0 && (uint32_t)ahead < d.da_len) {   // da.rs:167-174
+                        const uint32_t id = (uint32_t)(-na.x);
+                        if (nh == 0) { h01.x = id; h01.y = nch; }
+                        else if (nh == 1) { h01.z = id; h01.w = nch; }
+                        else if (nh == 2) { h23.x = id; h23.y = nch; }
+                        else if (nh == 3) { h23.z = id; h23.w = nch; }
+                        else {
+                            const uint32_t k = (uint32_t)d.dup[id] + 1;      // index.rs:46-51
+                            total += k;
+                            atomicAdd(&bcount[b + nch], k);
+                        }
+                        nh++;
+                    }
+                    prev = q;
+                    q = q2;
+                    nq = nq2;
+                    c = c1;
+                    c1 = c2;
+                    i = i2;
+                }
+                // duplicate counts of the remembered hits: independent loads, off the walk's chain
+                const uint32_t k0 = nh > 0 ? (uint32_t)d.dup[h01.x] + 1 : 0u;
+                const uint32_t k1 = nh > 1 ? (uint32_t)d.dup[h01.z] + 1 : 0u;
+                const uint32_t k2 = nh > 2 ? (uint32_t)d.dup[h23.x] + 1 : 0u;
+                const uint32_t k3 = nh > 3 ? (uint32_t)d.dup[h23.z] + 1 : 0u;
+                total += k0 + k1 + k2 + k3;
+                if (nh > 0) { atomicAdd(&bcount[b + h01.y], k0); h01.y |= (k0 - 1) << 16; }
+                if (nh > 1) { atomicAdd(&bcount[b + h01.w], k1); h01.w |= (k1 - 1) << 16; }
+                if (nh > 2) { atomicAdd(&bcount[b + h23.y], k2); h23.y |= (k2 - 1) << 16; }
+                if (nh > 3) { atomicAdd(&bcount[b + h23.w], k3); h23.w |= (k3 - 1) << 16; }
+                nhit[b] = (uint8_t)min(nh, 255u);
+                if (nh > 0) hits[2 * (size_t)b] = h01;
+                if (nh > 2) hits[2 * (size_t)b + 1] = h23;
             } else if (d.da_len > KP_ROOT_ID) {
                 nh = 0;
                 int prev = KP_ROOT_ID;
@@ -445,29 +600,24 @@ __global__ void __launch_bounds__(LAT_THREADS) kp_lattice_walk(const uint8_t* __
                         int2 na = d.da[ahead];
                         if (na.y == q && na.x < 0) {                         // da.rs:167-174
                             uint32_t id = (uint32_t)(-na.x);
-                            if (!FILL) {
-                                const uint32_t k = (uint32_t)d.dup[id] + 1;  // index.rs:46-51
-                                total += k;
-                                atomicAdd(&bcount[b + nch], k);
-                                if (nh == 0) { h01.x = id; h01.y = nch; }
-                                else if (nh == 1) { h01.z = id; h01.w = nch; }
-                                else if (nh == 2) { h23.x = id; h23.y = nch; }
-                                else if (nh == 3) { h23.z = id; h23.w = nch; }
-                            } else {
-                                expand(id, nch);
-                            }
+                            const uint32_t k = (uint32_t)d.dup[id] + 1;      // index.rs:46-51
+                            total += k;
+                            atomicAdd(&bcount[b + nch], k);
+                            const uint32_t y = nch | ((k - 1) << 16);
+                            if (nh == 0) { h01.x = id; h01.y = y; }
+                            else if (nh == 1) { h01.z = id; h01.w = y; }
+                            else if (nh == 2) { h23.x = id; h23.y = y; }
+                            else if (nh == 3) { h23.z = id; h23.w = y; }
                             nh++;
                         }
                     }
                     prev = q;
                     base = nq.x;
                 }
-                if (!FILL) {
-                    nhit[b] = (uint8_t)min(nh, 255u);
-                    if (nh > 0) hits[2 * (size_t)b] = h01;
-                    if (nh > 2) hits[2 * (size_t)b + 1] = h23;
-                }
-            } else if (!FILL) {
+                nhit[b] = (uint8_t)min(nh, 255u);
+                if (nh > 0) hits[2 * (size_t)b] = h01;
+                if (nh > 2) hits[2 * (size_t)b + 1] = h23;
+            } else {
                 nhit[b] = 0;
             }
             const bool matched = nh > 0;
@@ -480,12 +630,9 @@ __global__ void __launch_bounds__(LAT_THREADS) kp_lattice_walk(const uint8_t* __
                     atomicAdd(&ucount[bi.z], ci.unk_count);
                 } else {
                     uint32_t ulen = bi.z - b;
-                    for (uint32_t j = 0; j < ci.unk_count; j++) {
-                        short4 m = d.unk_morphs[ci.unk_first + j - 1];       // lattice.rs:195
-                        rec[o++] = make_uint4((uint32_t)(ci.unk_first + j) | ((uint32_t)KP_CLASS_UNKNOWN << KP_KIND_SHIFT),
-                                              b, (uint32_t)(uint16_t)m.x | ((uint32_t)(uint16_t)m.y << 16),
-                                              (uint32_t)(uint16_t)m.z | (ulen << 16));
-                    }
+                    for (uint32_t j = 0; j < ci.unk_count; j++)             // lattice.rs:195
+                        rec[o++] = kp_node_rec((uint32_t)(ci.unk_first + j), KP_CLASS_UNKNOWN, b,
+                                               ld_morph(d.unk_morphs, ci.unk_first + j - 1), ulen);
                 }
             }
         }
@@ -586,6 +733,9 @@ int kp_launch_column_order(const kp_chunk& c, const kp_ddict& d, const kp_perm& 
 #define KP_SENT_THREADS 64
 #endif
 constexpr int SENT_THREADS = KP_SENT_THREADS;   // one warp per sentence
+#ifndef KP_BK_PIPE
+#define KP_BK_PIPE 1
+#endif
 constexpr uint32_t BK_SMEM = 512;   // boundaries per sentence whose fill cursors fit in shared memory
 
 __global__ void __launch_bounds__(SENT_THREADS) kp_bucketize(uint32_t S, const uint32_t* __restrict__ coff,
@@ -626,6 +776,59 @@ __global__ void __launch_bounds__(SENT_THREADS) kp_bucketize(uint32_t S, const u
         for (uint32_t p = lane; p <= n; p += 32) sfill[p] = make_uint2(0u, 0u);
         __syncwarp();
     }
+#if KP_BK_PIPE
+    // Software pipeline, two rounds deep: the node records of round k+2 and the gathers that depend on
+    // the records of round k+1 (bucket base, and for unknown nodes the known count and first id of
+    // the class) are in flight while round k does its ranking and stores.
+    auto gather = [&](const uint4& r, bool valid, uint32_t& base, uint32_t& uslot) {
+        base = 0;
+        uslot = 0;
+        if (valid) {
+            const uint32_t e = r.y + (r.w >> 16);
+            base = boff[e];
+            if ((r.x >> KP_KIND_SHIFT) != KP_CLASS_KNOWN) {
+                const uint32_t cat = binfo[r.y].w & 0xFFu;      // class of the node's first char = of all its chars
+                uslot = (bcount[e] - ucount[e]) + ((r.x & KP_ID_MASK) - (uint32_t)d.catinfo[cat].unk_first);
+            }
+        }
+    };
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    uint4 rcur = n0 + lane < n1 ? rec[n0 + lane] : zero4;
+    uint4 rnext = n0 + 32 + lane < n1 ? rec[n0 + 32 + lane] : zero4;
+    uint32_t gbase, guslot;
+    gather(rcur, n0 + lane < n1, gbase, guslot);
+    for (uint32_t i0 = n0; i0 < n1; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool valid = i < n1;
+        const uint4 r = rcur;
+        const uint32_t base = gbase, uslot = guslot;
+        rcur = rnext;
+        gather(rcur, i + 32 < n1, gbase, guslot);
+        rnext = i + 64 < n1 ? rec[i + 64] : zero4;
+        const uint32_t e = valid ? r.y + (r.w >> 16) : KP_NONE;   // end boundary = start + char_len (lattice.rs:187,200)
+        const bool known = valid && (r.x >> KP_KIND_SHIFT) == KP_CLASS_KNOWN;
+        const uint32_t m = __match_any_sync(KP_FULL, e);
+        const uint32_t km = m & __ballot_sync(KP_FULL, known);
+        const uint32_t leader = (uint32_t)__ffs(m) - 1;
+        uint2 old = make_uint2(0, 0);
+        if (valid && lane == leader) {
+            uint2* cur = insm ? &sfill[e - bb] : &bfill[e];
+            old = *cur;
+            *cur = make_uint2(old.x + (uint32_t)__popc(m), old.y + (uint32_t)__popc(km));
+        }
+        old.x = __shfl_sync(KP_FULL, old.x, leader);
+        old.y = __shfl_sync(KP_FULL, old.y, leader);
+        if (valid) {
+            const uint32_t first = e == bb ? 1u : 0u;       // BOS occupies slot 0 of the first bucket
+            bnode[base + first + old.x + (uint32_t)__popc(m & lanemask_lt())] = i;
+            // known: next free known slot; unknown: shared slot of (end boundary, unknown id)
+            const uint32_t slot = known ? base + first + old.y + (uint32_t)__popc(km & lanemask_lt()) : base + uslot;
+            red[slot] = make_int2(KP_INF, (int)((r.z >> 16) * (d.connT_stride * 2u)));   // byte offset of row right_id in connT
+            tgt[i] = make_uint2((uint32_t)perm[r.z & 0xFFFFu] | (r.w << 16), slot);   // left id as its column in connP
+        }
+        __syncwarp();
+    }
+#else
     uint4 rnext = n0 + lane < n1 ? rec[n0 + lane] : make_uint4(0, 0, 0, 0);   // one round ahead
     for (uint32_t i0 = n0; i0 < n1; i0 += 32) {
         uint32_t i = i0 + lane;
@@ -661,6 +864,7 @@ __global__ void __launch_bounds__(SENT_THREADS) kp_bucketize(uint32_t S, const u
         }
         __syncwarp();
     }
+#endif
 }
 
 int kp_launch_bucketize(const kp_chunk& c, const kp_ddict& d, const kp_perm& pm, cudaStream_t st) {
@@ -674,7 +878,16 @@ int kp_launch_bucketize(const kp_chunk& c, const kp_ddict& d, const kp_perm& pm,
 // =================================================================================================
 // Viterbi work order
 // =================================================================================================
-constexpr int VIT_GROUP = 8;
+#ifndef KP_VIT_PRED
+#define KP_VIT_PRED 1
+#endif
+#ifndef KP_VIT_GROUP
+#define KP_VIT_GROUP 8
+#endif
+#ifndef KP_VIT_MINB
+#define KP_VIT_MINB 12
+#endif
+constexpr int VIT_GROUP = KP_VIT_GROUP;
 constexpr int VIT_THREADS = 128;
 constexpr uint32_t LEN_BINS = 4096;
 
@@ -756,7 +969,7 @@ __device__ __forceinline__ int ld_conn(const char* p) {
 // nodes per sentence that lie on the best path.  dp goes to ndp[i] and is min-merged into the node's
 // reduced slot; the __syncwarp orders those stores before the next boundary's loads.
 // =================================================================================================
-__global__ void __launch_bounds__(VIT_THREADS, 12) kp_viterbi(
+__global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
     uint32_t S, const uint32_t* __restrict__ order, const uint32_t* __restrict__ coff, const uint32_t* __restrict__ noff,
     const uint32_t* __restrict__ boff, const uint32_t* __restrict__ rcnt, const uint2* __restrict__ tgt, int2* red,
     int32_t* __restrict__ ndp, int32_t* __restrict__ eos_cost, const int16_t* __restrict__ connT) {
@@ -794,7 +1007,9 @@ __global__ void __launch_bounds__(VIT_THREADS, 12) kp_viterbi(
         }
         const uint32_t T = t1 - t0;
         const uint32_t Tmax = __reduce_max_sync(KP_FULL, T), Rmax = __reduce_max_sync(KP_FULL, R);
+#if !KP_VIT_PRED
         const uint32_t qb = R ? rb : 0u, qlast = R ? rb + R - 1 : 0u;    // R == 0: harmless reads of entry 0
+#endif
         for (uint32_t tc = 0; tc < Tmax; tc += VIT_GROUP) {
             const bool tv = tc + l < T;
             uint2 tg = tgn;
@@ -804,6 +1019,20 @@ __global__ void __launch_bounds__(VIT_THREADS, 12) kp_viterbi(
                 crow = col_of(tg.x & 0xFFFFu);
             }
             int best = INT_MAX;
+#if KP_VIT_PRED
+            // lanes without a target and groups whose bucket is exhausted issue no loads at all: the
+            // loop bound is the warp's largest bucket, the memory traffic is each group's own
+            const uint32_t Rl = tv ? R : 0u;
+            for (uint32_t jj = 0; jj < Rmax; jj += 4) {
+#pragma unroll
+                for (uint32_t u = 0; u < 4; u++) {
+                    if (jj + u < Rl) {
+                        const int2 e = red[rb + jj + u];
+                        best = __viaddmin_s32(e.x, ld_conn(crow + (uint32_t)e.y), best);
+                    }
+                }
+            }
+#else
             for (uint32_t jj = 0; jj < Rmax; jj += 4) {
 #pragma unroll
                 for (uint32_t u = 0; u < 4; u++) {
@@ -811,6 +1040,7 @@ __global__ void __launch_bounds__(VIT_THREADS, 12) kp_viterbi(
                     best = __viaddmin_s32(e.x, ld_conn(crow + (uint32_t)e.y), best);
                 }
             }
+#endif
             if (tv) {
                 int dp = KP_INF;
                 if (R) dp = min(best + (int)(int16_t)(tg.x >> 16), KP_INF);
@@ -907,7 +1137,11 @@ constexpr int BT_THREADS = 128;
 #endif
 constexpr int BT_GROUP = KP_BT_GROUP;
 
-__global__ void __launch_bounds__(BT_THREADS) kp_backtrace_find(uint32_t S, const uint32_t* __restrict__ coff,
+#ifndef KP_BT_ORDER
+#define KP_BT_ORDER 1
+#endif
+__global__ void __launch_bounds__(BT_THREADS) kp_backtrace_find(uint32_t S, const uint32_t* __restrict__ order,
+                                                                const uint32_t* __restrict__ coff,
                                                                 const uint32_t* __restrict__ noff,
                                                                 const uint32_t* __restrict__ boff,
                                                                 const uint4* __restrict__ rec,
@@ -916,8 +1150,11 @@ __global__ void __launch_bounds__(BT_THREADS) kp_backtrace_find(uint32_t S, cons
                                                                 const int16_t* __restrict__ conn, uint32_t conn_row,
                                                                 uint32_t* __restrict__ path,
                                                                 uint32_t* __restrict__ tcount) {
-    const uint32_t s = (blockIdx.x * BT_THREADS + threadIdx.x) / BT_GROUP;
-    if (s >= S) return;                          // whole groups leave together
+    const uint32_t slot = (blockIdx.x * BT_THREADS + threadIdx.x) / BT_GROUP;
+    if (slot >= S) return;                       // whole groups leave together
+    // length order, longest first (the Viterbi work order): the groups of a warp walk paths of about
+    // the same length, and the long paths start first
+    const uint32_t s = KP_BT_ORDER ? order[slot] : slot;
     const uint32_t l = threadIdx.x & (BT_GROUP - 1), gshift = lane_id() & ~(uint32_t)(BT_GROUP - 1);
     const uint32_t gmask = ((1u << BT_GROUP) - 1u) << gshift;
     const uint32_t bb = coff[s] + s, n = coff[s + 1] - coff[s];
@@ -998,7 +1235,7 @@ __global__ void __launch_bounds__(BT_THREADS) kp_backtrace_emit(uint32_t S, cons
 
 int kp_launch_backtrace_count(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
     if (c.S == 0) return 0;
-    kp_backtrace_find<<<(uint32_t)(((uint64_t)c.S * BT_GROUP + BT_THREADS - 1) / BT_THREADS), BT_THREADS, 0, st>>>(c.S, c.coff, c.noff, c.boff, c.rec, c.ndp, c.bnode,
+    kp_backtrace_find<<<(uint32_t)(((uint64_t)c.S * BT_GROUP + BT_THREADS - 1) / BT_THREADS), BT_THREADS, 0, st>>>(c.S, c.order, c.coff, c.noff, c.boff, c.rec, c.ndp, c.bnode,
                                                          d.conn, d.conn_row, c.path, c.tcount);
     return kp_launch_check("kp_backtrace_find");
 }

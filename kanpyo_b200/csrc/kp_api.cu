@@ -89,7 +89,7 @@ struct kp_tokenizer {
     uint32_t perm_age = 0;     // passes since the column order was last ranked
     DevBuf perm_hist, perm_map, perm_conn;
     // chunk scratch
-    DevBuf text, off, nchar, coff, binfo, ncount, noff, bcount, boff, ucount, rcnt, nhit, hits, bfill, rec, tgt, red, ndp, bnode, path, pre, lenhist, order,
+    DevBuf text, off, nchar, coff, binfo, ncount, noff, bcount, boff, ucount, rbk, nhit, hits, bfill, rec, tgt, red, ndp, bnode, path, pre, lenhist, order,
         tcount, toff32, scan_tmp, totals, err;
     // device outputs
     DevBuf d_tok_off, d_tokens, d_eos;
@@ -172,7 +172,7 @@ int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_token
     KP_TRY(t->ucount.ensure(sizeof(uint32_t) * (NB + 1)));
     KP_TRY(t->nhit.ensure(NB + 16));
     KP_TRY(t->hits.ensure(sizeof(uint4) * 2 * (NB + 1)));
-    KP_TRY(t->rcnt.ensure(sizeof(uint32_t) * (NB + 1)));
+    KP_TRY(t->rbk.ensure(sizeof(uint2) * (NB + 1)));
     KP_TRY(t->scan_tmp.ensure(sizeof(uint64_t) * kp_scan_tmp_elems((uint32_t)NB + 1)));
     c.scan_tmp = t->scan_tmp.as<uint64_t>();
     c.binfo = t->binfo.as<uint4>();
@@ -184,7 +184,7 @@ int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_token
     c.ucount = t->ucount.as<uint32_t>();
     c.nhit = t->nhit.as<uint8_t>();
     c.hits = t->hits.as<uint4>();
-    c.rcnt = t->rcnt.as<uint32_t>();
+    c.rbk = t->rbk.as<uint2>();
 
     KP_LAUNCH(kp_launch_prep_fill(c, d, st));
     KP_LAUNCH(kp_launch_length_order(c, st));        // work order of the Viterbi sweep (needs only coff)
@@ -193,7 +193,7 @@ int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_token
     KP_LAUNCH(kp_launch_scan2(c.ncount, c.bcount, c.noff, c.boff, c.NB, c.scan_tmp, &c.totals[1], &c.totals[2], st));
     KP_CUDA(cudaMemcpyAsync(h_tot, c.totals, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaStreamSynchronize(st));
-    if (h_tot[1] >= (1ull << 32) - 1) return KP_ERR_TOO_LARGE;
+    if (h_tot[1] >= (1ull << 31) - 1) return KP_ERR_TOO_LARGE;   // node indices carry a flag in bit 31 (KP_SLOT_SHARED)
     c.N = (uint32_t)h_tot[1];
     if (h_tot[2] != h_tot[1]) {
         kp_set_error("internal: bucket entries %llu != nodes %llu", (unsigned long long)h_tot[2],
@@ -307,7 +307,7 @@ extern "C" void kp_tokenizer_destroy(kp_tokenizer* t) {
     cudaSetDevice(t->device);
     if (t->stream) cudaStreamSynchronize(t->stream);
     DevBuf* bufs[] = {&t->text, &t->off, &t->nchar, &t->coff, &t->binfo, &t->ncount, &t->noff, &t->bcount, &t->boff,
-                      &t->bfill, &t->ucount, &t->rcnt, &t->nhit, &t->hits, &t->rec, &t->tgt, &t->red, &t->ndp, &t->bnode, &t->path, &t->pre, &t->lenhist, &t->order, &t->tcount, &t->toff32,
+                      &t->bfill, &t->ucount, &t->rbk, &t->nhit, &t->hits, &t->rec, &t->tgt, &t->red, &t->ndp, &t->bnode, &t->path, &t->pre, &t->lenhist, &t->order, &t->tcount, &t->toff32,
                       &t->scan_tmp, &t->totals, &t->err, &t->d_tok_off, &t->d_tokens, &t->d_eos, &t->perm_hist, &t->perm_map,
                       &t->perm_conn};
     for (DevBuf* b : bufs) b->release();

@@ -12,6 +12,7 @@ constexpr int KP_ROOT_ID = 1;                  // kanpyo-dict/src/trie/da.rs:9
 constexpr int KP_INF = 1 << 30;                // src/lattice.rs:117
 constexpr uint32_t KP_MAX_UNKNOWN_LEN = 1024;  // src/lattice.rs:55
 constexpr uint32_t KP_NONE = 0xFFFFFFFFu;      // Option::None for slot / node indices
+constexpr uint32_t KP_SLOT_SHARED = 0x80000000u;   // tgt.y: the reduced slot is shared (unknown node); nodes per chunk < 2^31
 
 // first-character table of the trie walk (kp_dict.cu): code points it covers, and its two markers
 constexpr uint32_t KP_FIRST_CPS = 0x10000u;

@@ -394,7 +394,7 @@ constexpr uint32_t LAT_HITS = 4;   // trie hits per start boundary remembered fr
 #define KP_WALK_T1 1
 #endif
 #ifndef KP_CNT_MINB
-#define KP_CNT_MINB 6
+#define KP_CNT_MINB 8
 #endif
 #ifndef KP_FILL_MINB
 #define KP_FILL_MINB 5
@@ -746,7 +746,7 @@ __global__ void __launch_bounds__(SENT_THREADS) kp_bucketize(uint32_t S, const u
                                                              const uint4* __restrict__ binfo,
                                                              const uint4* __restrict__ rec, kp_ddict d,
                                                              const uint16_t* __restrict__ perm,
-                                                             uint2* __restrict__ bfill, uint32_t* __restrict__ rcnt,
+                                                             uint2* __restrict__ bfill, uint2* __restrict__ rbk,
                                                              uint2* __restrict__ tgt, int2* __restrict__ red,
                                                              uint32_t* __restrict__ bnode) {
     uint32_t s = (blockIdx.x * SENT_THREADS + threadIdx.x) >> 5;
@@ -760,7 +760,7 @@ __global__ void __launch_bounds__(SENT_THREADS) kp_bucketize(uint32_t S, const u
         const uint32_t uc = ucount[b];
         uint32_t r = bcount[b] - uc;
         if (uc) r += d.catinfo[binfo[b - 1].w & 0xFFu].unk_count;   // uc > 0 implies p > 0
-        rcnt[b] = r;
+        rbk[b] = make_uint2(boff[b], r);
     }
     if (lane == 0) {
         uint32_t q = boff[bb];                          // BOS: dp None -> unwrap_or(0) (lattice.rs:127)
@@ -823,8 +823,9 @@ __global__ void __launch_bounds__(SENT_THREADS) kp_bucketize(uint32_t S, const u
             bnode[base + first + old.x + (uint32_t)__popc(m & lanemask_lt())] = i;
             // known: next free known slot; unknown: shared slot of (end boundary, unknown id)
             const uint32_t slot = known ? base + first + old.y + (uint32_t)__popc(km & lanemask_lt()) : base + uslot;
-            red[slot] = make_int2(KP_INF, (int)((r.z >> 16) * (d.connT_stride * 2u)));   // byte offset of row right_id in connT
-            tgt[i] = make_uint2((uint32_t)perm[r.z & 0xFFFFu] | (r.w << 16), slot);   // left id as its column in connP
+            red[slot] = make_int2(KP_INF, (int)((r.z >> 16) * d.connT_stride));       // {dp, element offset of row right_id in connT}
+            tgt[i] = make_uint2((uint32_t)perm[r.z & 0xFFFFu] | (r.w << 16),           // left id as its column in connP
+                                known ? slot : slot | KP_SLOT_SHARED);
         }
         __syncwarp();
     }
@@ -859,8 +860,9 @@ __global__ void __launch_bounds__(SENT_THREADS) kp_bucketize(uint32_t S, const u
                 const uint32_t cat = binfo[r.y].w & 0xFFu;  // class of the node's first char = of all its chars
                 slot = base + (bcount[e] - ucount[e]) + ((r.x & KP_ID_MASK) - (uint32_t)d.catinfo[cat].unk_first);
             }
-            red[slot] = make_int2(KP_INF, (int)((r.z >> 16) * (d.connT_stride * 2u)));   // byte offset of row right_id in connT
-            tgt[i] = make_uint2((uint32_t)perm[r.z & 0xFFFFu] | (r.w << 16), slot);   // left id as its column in connP
+            red[slot] = make_int2(KP_INF, (int)((r.z >> 16) * d.connT_stride));       // {dp, element offset of row right_id in connT}
+            tgt[i] = make_uint2((uint32_t)perm[r.z & 0xFFFFu] | (r.w << 16),           // left id as its column in connP
+                                known ? slot : slot | KP_SLOT_SHARED);
         }
         __syncwarp();
     }
@@ -871,22 +873,23 @@ int kp_launch_bucketize(const kp_chunk& c, const kp_ddict& d, const kp_perm& pm,
     if (c.S == 0) return 0;
     uint32_t blocks = (uint32_t)(((uint64_t)c.S * 32 + SENT_THREADS - 1) / SENT_THREADS);
     kp_bucketize<<<blocks, SENT_THREADS, 0, st>>>(c.S, c.coff, c.noff, c.boff, c.bcount, c.ucount, c.binfo, c.rec, d,
-                                                  pm.perm, c.bfill, c.rcnt, c.tgt, c.red, c.bnode);
+                                                  pm.perm, c.bfill, c.rbk, c.tgt, c.red, c.bnode);
     return kp_launch_check("kp_bucketize");
 }
 
 // =================================================================================================
 // Viterbi work order
 // =================================================================================================
-#ifndef KP_VIT_PRED
-#define KP_VIT_PRED 1
-#endif
 #ifndef KP_VIT_GROUP
 #define KP_VIT_GROUP 8
 #endif
 #ifndef KP_VIT_MINB
-#define KP_VIT_MINB 12
+#define KP_VIT_MINB 10
 #endif
+#ifndef KP_VIT_UNROLL
+#define KP_VIT_UNROLL 4
+#endif
+constexpr int VIT_UNROLL = KP_VIT_UNROLL;     // pairs per batch of the inner loop
 constexpr int VIT_GROUP = KP_VIT_GROUP;
 constexpr int VIT_THREADS = 128;
 constexpr uint32_t LEN_BINS = 4096;
@@ -949,6 +952,21 @@ int kp_launch_length_order(const kp_chunk& c, cudaStream_t st) {
     return rc < 0 ? rc : 3;
 }
 
+// &base[i] of an int16 array, computed once and kept: `volatile` stops the compiler from recomputing
+// it from its inputs at every use inside the pair loop
+__device__ __forceinline__ uint64_t elem_ptr_pinned(const int16_t* base, uint32_t i) {
+    uint64_t r;
+    asm volatile("mad.wide.u32 %0, %1, 2, %2;" : "=l"(r) : "r"(i), "l"(base));
+    return r;
+}
+// *(int16*)(p + 2 * off): address = one IMAD.WIDE with an immediate multiplier
+__device__ __forceinline__ int ld_conn_at(uint64_t p, uint32_t off) {
+    uint64_t a;
+    int v;
+    asm("mad.wide.u32 %0, %1, 2, %2;" : "=l"(a) : "r"(off), "l"(p));
+    asm("ld.global.nc.s16 %0, [%1];" : "=r"(v) : "l"(a));
+    return v;
+}
 __device__ __forceinline__ int ld_conn(const char* p) {
     int v;
     asm("ld.global.nc.s16 %0, [%1];" : "=r"(v) : "l"(p));
@@ -958,20 +976,26 @@ __device__ __forceinline__ int ld_conn(const char* p) {
 // =================================================================================================
 // Viterbi forward sweep (lattice.rs:116-143, dp values only).
 //
-// A warp carries 4 sentences (taken in length order), 8 lanes each, and steps all of them boundary
-// by boundary with warp-uniform loop bounds, so the four groups share every issued instruction.
-// Lanes hold the nodes STARTING at the boundary (targets); each lane folds the boundary's reduced
-// bucket (predecessors) with one DPX add-min per pair:
+// A warp carries 32 / VIT_GROUP sentences (taken in length order), VIT_GROUP lanes each, and steps all
+// of them boundary by boundary with warp-uniform loop bounds, so the groups share every issued
+// instruction.  Lanes hold the nodes STARTING at the boundary (targets); each lane folds the
+// boundary's reduced bucket (predecessors) with one DPX add-min per pair:
 //   best = min(best, dp[j] + conn(right_j, left_i))                                 connection.rs:12-14
 //   dp[i] = min(best + cost_i, INF), kept only if < INF                             lattice.rs:127-139
-// Out-of-range predecessor slots are clamped to the bucket's last entry: a duplicate never changes a
-// minimum.  The argmin (pre_nodes) is NOT tracked here: the back-trace recomputes it for the ~30
-// nodes per sentence that lie on the best path.  dp goes to ndp[i] and is min-merged into the node's
-// reduced slot; the __syncwarp orders those stores before the next boundary's loads.
+// The loop bound is the warp's largest bucket; lanes without a target and groups whose own bucket is
+// exhausted have their loads predicated off, so the memory traffic is each group's own.  Per pair
+// the loop issues five instructions: predicate, 8-byte bucket entry at an immediate offset, row
+// address (one IMAD.WIDE), 2-byte matrix cell, VIADDMNMX.
+// The argmin (pre_nodes) is NOT tracked here: the back-trace recomputes it for the ~30 nodes per
+// sentence that lie on the best path.  dp goes to ndp[i] and into the node's reduced slot: a plain
+// store for a known node (the slot is its own), a min-merge for an unknown node (the slot is shared
+// by every unknown node with that id ending there); the value to merge with is fetched before the
+// pair loop so its latency hides behind it.  The __syncwarp orders those stores before the next
+// boundary's loads.
 // =================================================================================================
 __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
     uint32_t S, const uint32_t* __restrict__ order, const uint32_t* __restrict__ coff, const uint32_t* __restrict__ noff,
-    const uint32_t* __restrict__ boff, const uint32_t* __restrict__ rcnt, const uint2* __restrict__ tgt, int2* red,
+    const uint2* __restrict__ rbk, const uint2* __restrict__ tgt, int2* red,
     int32_t* __restrict__ ndp, int32_t* __restrict__ eos_cost, const int16_t* __restrict__ connT) {
     const uint32_t slot = (blockIdx.x * VIT_THREADS + threadIdx.x) / VIT_GROUP;
     const uint32_t l = threadIdx.x & (VIT_GROUP - 1);
@@ -983,75 +1007,68 @@ __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
         n = coff[s + 1] - coff[s];
     }
     const uint32_t steps = __reduce_max_sync(KP_FULL, has ? n + 1 : 0u);
-    uint32_t t0 = 0, t1n = 0, rbn = 0, rn = 0;
+    uint32_t t0 = 0, t1n = 0;
+    uint2 bkn = make_uint2(0u, 0u);               // {first entry, entries} of the next boundary's reduced bucket
     if (has) {
         t0 = noff[bb];
         t1n = noff[bb + 1];
-        rbn = boff[bb];
-        rn = rcnt[bb];
+        bkn = rbk[bb];
     }
     // connT[right_j][left_i] (connection.rs:12-14, transposed): the lanes of a group share the row of
     // predecessor j and differ in the column, and the left ids of the nodes starting at one boundary
     // cluster (noun / unknown-word ids are neighbours), so a group's gather touches ~2 lines, not ~5
-    auto col_of = [&](uint32_t left) -> const char* { return (const char*)connT + left * 2u; };
     uint2 tgn = make_uint2(0u, KP_NONE);          // first target chunk of the next boundary, prefetched
     if (has && t0 + l < t1n) tgn = tgt[t0 + l];
-    const char* crown = col_of(tgn.x & 0xFFFFu);
     for (uint32_t p = 0; p < steps; p++) {
         const bool act = has && p <= n;
-        const uint32_t t1 = act ? t1n : t0, rb = rbn, R = act ? rn : 0u;
+        const uint32_t t1 = act ? t1n : t0, R = act ? bkn.y : 0u;
+        const int2* const rbase = red + bkn.x;
         if (has && p < n) {                       // bounds of the next boundary, off the critical path
             t1n = noff[bb + p + 2];
-            rbn = boff[bb + p + 1];
-            rn = rcnt[bb + p + 1];
+            bkn = rbk[bb + p + 1];
         }
         const uint32_t T = t1 - t0;
         const uint32_t Tmax = __reduce_max_sync(KP_FULL, T), Rmax = __reduce_max_sync(KP_FULL, R);
-#if !KP_VIT_PRED
-        const uint32_t qb = R ? rb : 0u, qlast = R ? rb + R - 1 : 0u;    // R == 0: harmless reads of entry 0
-#endif
         for (uint32_t tc = 0; tc < Tmax; tc += VIT_GROUP) {
             const bool tv = tc + l < T;
             uint2 tg = tgn;
-            const char* crow = crown;
-            if (tc) {
-                tg = tv ? tgt[t0 + tc + l] : make_uint2(0u, KP_NONE);
-                crow = col_of(tg.x & 0xFFFFu);
-            }
+            if (tc) tg = tv ? tgt[t0 + tc + l] : make_uint2(0u, KP_NONE);
+            const uint64_t crow = elem_ptr_pinned(connT, tg.x & 0xFFFFu);   // this target's column; entries carry row offsets
+            // reduced slot: bit 31 marks a shared one (unknown node); KP_NONE = EOS, which ends nowhere
+            const bool eos = tg.y == KP_NONE;
+            int* const slotp = &red[tg.y & ~KP_SLOT_SHARED].x;
+            int merged = KP_INF;
+            if (tv && !eos && (tg.y & KP_SLOT_SHARED)) merged = *slotp;
             int best = INT_MAX;
-#if KP_VIT_PRED
-            // lanes without a target and groups whose bucket is exhausted issue no loads at all: the
-            // loop bound is the warp's largest bucket, the memory traffic is each group's own
-            const uint32_t Rl = tv ? R : 0u;
-            for (uint32_t jj = 0; jj < Rmax; jj += 4) {
+            const int2* rp = rbase;
+            int rem = tv ? (int)R : 0;
+            for (uint32_t jj = 0; jj < Rmax; jj += VIT_UNROLL) {
+                // all bucket entries of the batch first, then all matrix cells: two load latencies per
+                // batch, not two per pair
+                int2 e[VIT_UNROLL];
+                int cell[VIT_UNROLL];
 #pragma unroll
-                for (uint32_t u = 0; u < 4; u++) {
-                    if (jj + u < Rl) {
-                        const int2 e = red[rb + jj + u];
-                        best = __viaddmin_s32(e.x, ld_conn(crow + (uint32_t)e.y), best);
-                    }
-                }
-            }
-#else
-            for (uint32_t jj = 0; jj < Rmax; jj += 4) {
+                for (int u = 0; u < VIT_UNROLL; u++)
+                    if (u < rem) e[u] = rp[u];
 #pragma unroll
-                for (uint32_t u = 0; u < 4; u++) {
-                    const int2 e = red[min(qb + jj + u, qlast)];
-                    best = __viaddmin_s32(e.x, ld_conn(crow + (uint32_t)e.y), best);
-                }
+                for (int u = 0; u < VIT_UNROLL; u++)
+                    if (u < rem) cell[u] = ld_conn_at(crow, (uint32_t)e[u].y);   // one IMAD.WIDE: crow + 2 * offset
+#pragma unroll
+                for (int u = 0; u < VIT_UNROLL; u++)
+                    if (u < rem) best = __viaddmin_s32(e[u].x, cell[u], best);
+                rp += VIT_UNROLL;
+                rem -= VIT_UNROLL;
             }
-#endif
             if (tv) {
                 int dp = KP_INF;
                 if (R) dp = min(best + (int)(int16_t)(tg.x >> 16), KP_INF);
                 ndp[t0 + tc + l] = dp;
-                if (tg.y == KP_NONE) eos_cost[s] = dp;
-                else red[tg.y].x = min(red[tg.y].x, dp);     // shared slots keep the minimum
+                if (eos) eos_cost[s] = dp;
+                else *slotp = min(merged, dp);
             }
         }
         // the next boundary's first targets: the address does not depend on this step's results
         tgn = (has && p < n && t1 + l < t1n) ? tgt[t1 + l] : make_uint2(0u, KP_NONE);
-        crown = col_of(tgn.x & 0xFFFFu);
         __syncwarp();
         t0 = t1;
     }
@@ -1060,7 +1077,7 @@ __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
 int kp_launch_viterbi(const kp_chunk& c, const kp_ddict& d, const kp_perm& pm, cudaStream_t st) {
     if (c.S == 0) return 0;
     uint32_t blocks = (uint32_t)(((uint64_t)c.S * VIT_GROUP + VIT_THREADS - 1) / VIT_THREADS);
-    kp_viterbi<<<blocks, VIT_THREADS, 0, st>>>(c.S, c.order, c.coff, c.noff, c.boff, c.rcnt, c.tgt, c.red, c.ndp,
+    kp_viterbi<<<blocks, VIT_THREADS, 0, st>>>(c.S, c.order, c.coff, c.noff, c.rbk, c.tgt, c.red, c.ndp,
                                                c.eos_cost, pm.connP);
     return kp_launch_check("kp_viterbi");
 }

@@ -39,7 +39,7 @@ struct kp_chunk {
     // scratch (device)
     uint32_t* nchar;  uint32_t* coff;
     uint4* binfo;
-    uint32_t* ncount; uint32_t* noff; uint32_t* bcount; uint32_t* boff; uint32_t* ucount; uint32_t* rcnt;
+    uint32_t* ncount; uint32_t* noff; uint32_t* bcount; uint32_t* boff; uint32_t* ucount; uint2* rbk;
     uint8_t* nhit; uint4* hits;   // per start boundary: trie hits seen by the counting walk, and the first 4 {id, chars}
     uint2* bfill;            // running {all, known} counts while bucketizing
     uint4* rec; uint2* tgt; int2* red; int32_t* ndp; uint32_t* bnode; uint32_t* path; uint32_t* pre;

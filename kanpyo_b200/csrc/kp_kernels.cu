@@ -736,9 +736,15 @@ constexpr int SENT_THREADS = KP_SENT_THREADS;   // one warp per sentence
 #ifndef KP_BK_PIPE
 #define KP_BK_PIPE 1
 #endif
-constexpr uint32_t BK_SMEM = 512;   // boundaries per sentence whose fill cursors fit in shared memory
+#ifndef KP_BK_SMEM
+#define KP_BK_SMEM 256
+#endif
+#ifndef KP_BK_MINB
+#define KP_BK_MINB 32          // 32 registers, 2 KB of cursors per warp: 64 resident warps per SM
+#endif
+constexpr uint32_t BK_SMEM = KP_BK_SMEM;   // boundaries per sentence whose fill cursors fit in shared memory
 
-__global__ void __launch_bounds__(SENT_THREADS) kp_bucketize(uint32_t S, const uint32_t* __restrict__ coff,
+__global__ void __launch_bounds__(SENT_THREADS, KP_BK_MINB) kp_bucketize(uint32_t S, const uint32_t* __restrict__ coff,
                                                              const uint32_t* __restrict__ noff,
                                                              const uint32_t* __restrict__ boff,
                                                              const uint32_t* __restrict__ bcount,

@@ -384,9 +384,6 @@ int kp_launch_prep_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
 constexpr int LAT_THREADS = KP_LAT_THREADS;
 
 constexpr uint32_t LAT_HITS = 4;   // trie hits per start boundary remembered from the counting walk
-#ifndef KP_WALK_ILP
-#define KP_WALK_ILP 1
-#endif
 #ifndef KP_FILL_FLAT
 #define KP_FILL_FLAT 1
 #endif
@@ -508,79 +505,6 @@ __global__ void __launch_bounds__(LAT_THREADS, FILL ? KP_FILL_MINB : KP_CNT_MINB
             } else if (FILL) {
                 if (d.da_len > KP_ROOT_ID)
                     o = kp_fill_rewalk(text, bp, send, b, kp_trie_view{d.da, d.da_len, d.dup, d.morphs}, rec, o);
-            } else if (!WORK && KP_WALK_ILP && d.da_len > KP_ROOT_ID) {
-                // Counting walk with the loads of one step issued together: the terminator probe
-                // da[base[q]] and the next transition da[base[q] + next byte] depend only on da[q]
-                // (da.rs:160-174), and the next text byte is fetched a step ahead.  A failed range
-                // test is carried as check = -1, which no state index equals.
-                const int2 dead = make_int2(0, -1);
-                uint32_t i = bp, nch = 0;
-                uint32_t c = text[i];
-                int prev = KP_ROOT_ID, q;
-                int2 nq = dead;
-                int2 f = make_int2(KP_FIRST_SLOW, 0);
-                if (KP_WALK_T1 && c < 0xF0u) {
-                    // the whole first character in one lookup (table built in kp_dict.cu); the text is
-                    // valid UTF-8, so the continuation bytes are inside the sentence
-                    uint32_t cp = c, L = 1;
-                    if (c >= 0xE0u) { cp = ((c & 0x0Fu) << 12) | ((text[i + 1] & 0x3Fu) << 6) | (text[i + 2] & 0x3Fu); L = 3; }
-                    else if (c >= 0x80u) { cp = ((c & 0x1Fu) << 6) | (text[i + 1] & 0x3Fu); L = 2; }
-                    f = d.first[cp];
-                    if (f.x != KP_FIRST_SLOW) {          // arrive in state f.x as if by its last byte
-                        i += L - 1;
-                        nch = 1;
-                        c = 0x80u;                       // counted already
-                        prev = 0;
-                        q = f.x;
-                        nq = f.x >= 0 ? make_int2(f.y, 0) : dead;
-                    }
-                }
-                if (f.x == KP_FIRST_SLOW) {
-                    q = d.da[KP_ROOT_ID].x + (int)c;                         // da.rs:160
-                    nq = (uint32_t)q < d.da_len ? d.da[q] : dead;            // Vec::get -> None (da.rs:161)
-                }
-                uint32_t c1 = i + 1 < send ? text[i + 1] : 0u;
-                while (nq.y == prev) {                                       // da.rs:162-164
-                    nch += !is_cont(c);
-                    const int ahead = nq.x;                                  // + TERMINATOR (0), da.rs:165
-                    const int q2 = nq.x + (int)c1;
-                    const uint32_t i2 = i + 1;
-                    const int2 na = (uint32_t)ahead < d.da_len ? d.da[ahead] : dead;
-                    const int2 nq2 = (i2 < send && (uint32_t)q2 < d.da_len) ? d.da[q2] : dead;
-                    const uint32_t c2 = i2 + 1 < send ? text[i2 + 1] : 0u;
-                    if (na.y == q && na.x < 0 && (uint32_t)ahead < d.da_len) {   // da.rs:167-174
-                        const uint32_t id = (uint32_t)(-na.x);
-                        if (nh == 0) { h01.x = id; h01.y = nch; }
-                        else if (nh == 1) { h01.z = id; h01.w = nch; }
-                        else if (nh == 2) { h23.x = id; h23.y = nch; }
-                        else if (nh == 3) { h23.z = id; h23.w = nch; }
-                        else {
-                            const uint32_t k = (uint32_t)d.dup[id] + 1;      // index.rs:46-51
-                            total += k;
-                            atomicAdd(&bcount[b + nch], k);
-                        }
-                        nh++;
-                    }
-                    prev = q;
-                    q = q2;
-                    nq = nq2;
-                    c = c1;
-                    c1 = c2;
-                    i = i2;
-                }
-                // duplicate counts of the remembered hits: independent loads, off the walk's chain
-                const uint32_t k0 = nh > 0 ? (uint32_t)d.dup[h01.x] + 1 : 0u;
-                const uint32_t k1 = nh > 1 ? (uint32_t)d.dup[h01.z] + 1 : 0u;
-                const uint32_t k2 = nh > 2 ? (uint32_t)d.dup[h23.x] + 1 : 0u;
-                const uint32_t k3 = nh > 3 ? (uint32_t)d.dup[h23.z] + 1 : 0u;
-                total += k0 + k1 + k2 + k3;
-                if (nh > 0) { atomicAdd(&bcount[b + h01.y], k0); h01.y |= (k0 - 1) << 16; }
-                if (nh > 1) { atomicAdd(&bcount[b + h01.w], k1); h01.w |= (k1 - 1) << 16; }
-                if (nh > 2) { atomicAdd(&bcount[b + h23.y], k2); h23.y |= (k2 - 1) << 16; }
-                if (nh > 3) { atomicAdd(&bcount[b + h23.w], k3); h23.w |= (k3 - 1) << 16; }
-                nhit[b] = (uint8_t)min(nh, 255u);
-                if (nh > 0) hits[2 * (size_t)b] = h01;
-                if (nh > 2) hits[2 * (size_t)b + 1] = h23;
             } else if (d.da_len > KP_ROOT_ID) {
                 nh = 0;
                 int prev = KP_ROOT_ID;
@@ -648,6 +572,124 @@ __global__ void __launch_bounds__(LAT_THREADS, FILL ? KP_FILL_MINB : KP_CNT_MINB
     }
 }
 
+// =================================================================================================
+// Counting walk, the production version (kp_lattice_walk<false, *> above is the plain statement of
+// the same walk; it still serves the work counters).  One thread per start boundary:
+//   * the first character is one lookup in the first-character table (kp_dict.cu);
+//   * per further byte, the terminator probe da[base[q]] and the next transition da[base[q] + byte]
+//     are issued together (both depend only on da[q], da.rs:160-174) and the text byte is fetched a
+//     step ahead; a failed range test clears `alive` instead of loading;
+//   * the first LAT_HITS hits {id, chars} go to a per-thread column of shared memory (no register
+//     rotation in the loop); their duplicate counts are looked up after the walk, off its chain.
+// The kernel is issue-bound with ~7 of 32 lanes live (walk lengths are heavy-tailed), so the loop is
+// kept to as few instructions as the compiler will give.
+// =================================================================================================
+__global__ void __launch_bounds__(LAT_THREADS, KP_CNT_MINB) kp_lattice_count(
+    const uint8_t* __restrict__ text, const uint4* __restrict__ binfo, uint32_t NB, kp_ddict d,
+    uint32_t* __restrict__ ncount, uint32_t* __restrict__ bcount, uint32_t* __restrict__ ucount,
+    uint8_t* __restrict__ nhit, uint4* __restrict__ hits) {
+    __shared__ uint2 sh_hit[LAT_HITS][LAT_THREADS];          // [slot][thread]: conflict-free columns
+    const uint32_t b = blockIdx.x * LAT_THREADS + threadIdx.x;
+    if (b >= NB) return;
+    const uint4 bi = binfo[b];
+    const uint32_t bp = bi.x, send = bi.y;
+    if (bp == send) {                            // EOS: one Dummy node (lattice.rs:165-175)
+        ncount[b] = 1;
+        return;
+    }
+    uint32_t nh = 0, total = 0;
+    if (d.da_len > KP_ROOT_ID) {
+        uint32_t i = bp;                         // index of the byte whose transition led to state q
+        const uint32_t c = text[i];
+        int prev = KP_ROOT_ID, q = 0;
+        int2 nq = make_int2(0, 0);
+        bool alive = false;
+        int2 f = make_int2(KP_FIRST_SLOW, 0);
+        if (KP_WALK_T1 && c < 0xF0u) {
+            // the text is valid UTF-8, so the continuation bytes are inside the sentence
+            uint32_t cp = c, L = 1;
+            if (c >= 0xE0u) { cp = ((c & 0x0Fu) << 12) | ((text[i + 1] & 0x3Fu) << 6) | (text[i + 2] & 0x3Fu); L = 3; }
+            else if (c >= 0x80u) { cp = ((c & 0x1Fu) << 6) | (text[i + 1] & 0x3Fu); L = 2; }
+            f = d.first[cp];
+            if (f.x != KP_FIRST_SLOW) {          // arrive in state f.x as if by the character's last byte
+                i += L - 1;
+                q = f.x;
+                alive = f.x >= 0;
+                nq = make_int2(f.y, 0);
+                prev = 0;
+            }
+        }
+        if (f.x == KP_FIRST_SLOW) {
+            q = d.da[KP_ROOT_ID].x + (int)c;                                 // da.rs:160
+            alive = (uint32_t)q < d.da_len;                                  // Vec::get -> None (da.rs:161)
+            if (alive) nq = d.da[q];
+        }
+        // chars among the bytes consumed so far, the one being tried included: exact whenever the
+        // transition held, which is the only time it is read
+        uint32_t nch = 1;
+        int c1 = i + 1 < send ? (int)(int8_t)text[i + 1] : 0;               // signed: continuation bytes are < -64
+        while (alive && nq.y == prev) {                                      // da.rs:162-164
+            const int ahead = nq.x;                                          // + TERMINATOR (0), da.rs:165
+            const int q2 = nq.x + (c1 & 0xFF);
+            const uint32_t i2 = i + 1;
+            const bool pa = (uint32_t)ahead < d.da_len;
+            const bool p2 = i2 < send && (uint32_t)q2 < d.da_len;
+            int2 na = make_int2(0, 0), nq2 = make_int2(0, 0);
+            if (pa) na = d.da[ahead];
+            if (p2) nq2 = d.da[q2];
+            int c2 = 0;
+            if (i2 + 1 < send) c2 = (int)(int8_t)text[i2 + 1];
+            if (pa && na.y == q && na.x < 0) {                               // da.rs:167-174
+                const uint32_t id = (uint32_t)(-na.x);
+                if (nh < LAT_HITS) {
+                    sh_hit[nh][threadIdx.x] = make_uint2(id, nch);
+                } else {
+                    const uint32_t k = (uint32_t)d.dup[id] + 1;              // index.rs:46-51
+                    total += k;
+                    atomicAdd(&bcount[b + nch], k);
+                }
+                nh++;
+            }
+            nch += c1 >= -64;                    // the byte tried next starts a character
+            prev = q;
+            q = q2;
+            nq = nq2;
+            alive = p2;
+            c1 = c2;
+            i = i2;
+        }
+        // duplicate counts of the remembered hits: independent loads, off the walk's chain
+        uint2 h[LAT_HITS];
+        uint32_t k[LAT_HITS];
+#pragma unroll
+        for (uint32_t u = 0; u < LAT_HITS; u++) {
+            h[u] = make_uint2(0u, 0u);
+            if (u < nh) h[u] = sh_hit[u][threadIdx.x];
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < LAT_HITS; u++) k[u] = u < nh ? (uint32_t)d.dup[h[u].x] + 1 : 0u;
+#pragma unroll
+        for (uint32_t u = 0; u < LAT_HITS; u++) {
+            if (u < nh) {
+                total += k[u];
+                atomicAdd(&bcount[b + h[u].y], k[u]);
+                h[u].y |= (k[u] - 1) << 16;
+            }
+        }
+        if (nh > 0) hits[2 * (size_t)b] = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y);
+        if (nh > 2) hits[2 * (size_t)b + 1] = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
+    }
+    nhit[b] = (uint8_t)min(nh, 255u);
+    // unknown words (lattice.rs:42-99)
+    const kp_catinfo ci = d.catinfo[bi.w & 0xFFu];
+    if ((nh == 0 || (ci.flags & 1u)) && ci.unk_count) {
+        total += ci.unk_count;
+        atomicAdd(&bcount[bi.z], ci.unk_count);
+        atomicAdd(&ucount[bi.z], ci.unk_count);
+    }
+    ncount[b] = total;
+}
+
 int kp_launch_lattice_count(const kp_chunk& c, const kp_ddict& d, bool count_work, cudaStream_t st) {
     if (c.NB == 0) return 0;
     uint32_t blocks = (c.NB + LAT_THREADS - 1) / LAT_THREADS;
@@ -655,8 +697,8 @@ int kp_launch_lattice_count(const kp_chunk& c, const kp_ddict& d, bool count_wor
         kp_lattice_walk<false, true><<<blocks, LAT_THREADS, 0, st>>>(c.text, c.binfo, c.NB, d, c.ncount, c.bcount, c.ucount,
                                                                 c.nhit, c.hits, nullptr, nullptr, c.totals);
     else
-        kp_lattice_walk<false, false><<<blocks, LAT_THREADS, 0, st>>>(c.text, c.binfo, c.NB, d, c.ncount, c.bcount, c.ucount,
-                                                                 c.nhit, c.hits, nullptr, nullptr, c.totals);
+        kp_lattice_count<<<blocks, LAT_THREADS, 0, st>>>(c.text, c.binfo, c.NB, d, c.ncount, c.bcount, c.ucount, c.nhit,
+                                                         c.hits);
     return kp_launch_check("kp_lattice_walk<count>");
 }
 

@@ -15,6 +15,6 @@ echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu > $OUT/ncu_launches_$TAG.log 2>&1
 echo "== ncu full (viterbi, lattice fill)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'kp_viterbi|kp_lattice_walk|kp_bucketize|kp_backtrace_find' -s 15 -c 5 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'kp_viterbi|kp_lattice_walk|kp_lattice_count|kp_bucketize|kp_backtrace_find' -s 15 -c 5 \
     -o $OUT/prof_$TAG -f python bench.py --steps 1 --warmup 3 --no-cpu > $OUT/ncu_full_$TAG.log 2>&1
 ls -la $OUT | tail -12

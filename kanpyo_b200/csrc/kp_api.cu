@@ -146,8 +146,10 @@ int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_token
     KP_CUDA(cudaEventRecord(t->ev[EV_H2D], st));
     KP_CUDA(cudaMemsetAsync(c.totals, 0, sizeof(uint64_t) * 8, st));
     KP_CUDA(cudaMemsetAsync(c.err, 0, sizeof(uint32_t) * 2, st));
+    KP_CUDA(cudaMemsetAsync(c.lenhist, 0, sizeof(uint32_t) * kp_len_bins(), st));
     KP_LAUNCH(kp_launch_prep_count(c, st));
     KP_LAUNCH(kp_launch_scan(c.nchar, c.coff, S, c.scan_tmp, &c.totals[0], st));
+    KP_LAUNCH(kp_launch_length_order(c, st));       // scan of the length histogram prep_count filled
     KP_CUDA(cudaMemcpyAsync(h_tot, c.totals, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaMemcpyAsync(h_err, c.err, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaStreamSynchronize(st));
@@ -186,8 +188,7 @@ int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_token
     c.hits = t->hits.as<uint4>();
     c.rbk = t->rbk.as<uint2>();
 
-    KP_LAUNCH(kp_launch_prep_fill(c, d, st));
-    KP_LAUNCH(kp_launch_length_order(c, st));        // work order of the Viterbi sweep (needs only coff)
+    KP_LAUNCH(kp_launch_prep_fill(c, d, st));        // boundary table + scatter of the Viterbi work order
     KP_CUDA(cudaEventRecord(t->ev[EV_PREP], st));
     KP_LAUNCH(kp_launch_lattice_count(c, d, t->count_work, st));
     KP_LAUNCH(kp_launch_scan2(c.ncount, c.bcount, c.noff, c.boff, c.NB, c.scan_tmp, &c.totals[1], &c.totals[2], st));

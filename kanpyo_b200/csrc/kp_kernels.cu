@@ -31,7 +31,7 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 }
 
 // =================================================================================================
-// Exclusive scans (3 launches: tile sums, scan of tile sums, apply).  Two arrays ride together.
+// Exclusive scans, one launch each (decoupled look-back).  Two arrays ride together.
 // =================================================================================================
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
@@ -39,110 +39,55 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 uint32_t kp_scan_tmp_elems(uint32_t n) { return 2 * ((n + SCAN_TILE - 1) / SCAN_TILE + 1); }
 
-__device__ __forceinline__ uint64_t block_reduce_u64(uint64_t v, uint64_t* sh) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(KP_FULL, v, o);
-    if (lane_id() == 0) sh[threadIdx.x >> 5] = v;
-    __syncthreads();
-    uint64_t r = 0;
-    if (threadIdx.x < 32) {
-        r = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0;
-        for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(KP_FULL, r, o);
+// Single pass: tile sums chained across blocks by decoupled look-back.
+// `state[t]` = flag << 62 | value: flag 1 = sum of tile t alone, flag 2 = sum of tiles 0..t.  Blocks take
+// their tile by ticket, so a block's predecessors are running or done.  One launch (plus a memset of
+// the state), the input read once.
+__device__ __forceinline__ uint64_t kp_scan_lookback(unsigned long long* state, uint32_t tile, uint64_t agg) {
+    // called by the 32 lanes of warp 0; returns the sum of tiles 0..tile-1
+    uint64_t excl = 0;
+    if (tile == 0) {
+        if (lane_id() == 0) atomicExch(&state[0], (2ull << 62) | agg);
+        return 0;
     }
-    return r;  // valid in thread 0
+    if (lane_id() == 0) atomicExch(&state[tile], (1ull << 62) | agg);
+    int32_t j0 = (int32_t)tile - 1;
+    while (true) {
+        const int32_t j = j0 - (int32_t)lane_id();
+        unsigned long long v = 2ull << 62;               // before tile 0: inclusive sum 0
+        if (j >= 0) {
+            do {
+                v = *(volatile unsigned long long*)&state[j];
+            } while ((v >> 62) == 0);
+        }
+        const uint32_t done = __ballot_sync(KP_FULL, (v >> 62) == 2);
+        const uint32_t upto = done ? (uint32_t)__ffs(done) - 1 : 31u;   // up to the nearest inclusive sum
+        uint64_t part = lane_id() <= upto ? (uint64_t)(v & ((1ull << 62) - 1)) : 0ull;
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(KP_FULL, part, o);
+        excl += __shfl_sync(KP_FULL, part, 0);
+        if (done) break;
+        j0 -= 32;
+    }
+    if (lane_id() == 0) atomicExch(&state[tile], (2ull << 62) | (excl + agg));
+    return excl;
 }
 
 template <bool TWO>
-__global__ void __launch_bounds__(SCAN_THREADS) kp_scan_tile_sums(const uint32_t* __restrict__ a,
-                                                                  const uint32_t* __restrict__ b, uint32_t n,
-                                                                  uint64_t* __restrict__ tmp, uint32_t ntiles) {
-    __shared__ uint64_t sh[SCAN_THREADS / 32];
-    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-    uint64_t sa = 0, sb = 0;
-    if (base + SCAN_ITEMS <= n) {                 // 32 contiguous, 32-byte aligned bytes per thread
-        const uint4 a0 = *(const uint4*)(a + base), a1 = *(const uint4*)(a + base + 4);
-        sa = (uint64_t)a0.x + a0.y + a0.z + a0.w + a1.x + a1.y + a1.z + a1.w;
-        if (TWO) {
-            const uint4 b0 = *(const uint4*)(b + base), b1 = *(const uint4*)(b + base + 4);
-            sb = (uint64_t)b0.x + b0.y + b0.z + b0.w + b1.x + b1.y + b1.z + b1.w;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; k++) {
-            uint32_t i = base + k;
-            if (i < n) {
-                sa += a[i];
-                if (TWO) sb += b[i];
-            }
-        }
-    }
-    uint64_t ra = block_reduce_u64(sa, sh);
-    if (threadIdx.x == 0) tmp[blockIdx.x] = ra;
-    if (TWO) {
-        __syncthreads();
-        uint64_t rb = block_reduce_u64(sb, sh);
-        if (threadIdx.x == 0) tmp[ntiles + blockIdx.x] = rb;
-    }
-}
-
-// one block: exclusive scan of the tile sums in place, totals out
-template <bool TWO>
-__global__ void __launch_bounds__(1024) kp_scan_partials(uint64_t* __restrict__ tmp, uint32_t ntiles,
-                                                         uint32_t* __restrict__ out_a, uint32_t* __restrict__ out_b,
-                                                         uint32_t n, uint64_t* __restrict__ total_a,
-                                                         uint64_t* __restrict__ total_b) {
-    __shared__ uint64_t wsum[32];
-    __shared__ uint64_t carry_sh;
-    for (int arr = 0; arr < (TWO ? 2 : 1); arr++) {
-        uint64_t* t = tmp + (size_t)arr * ntiles;
-        if (threadIdx.x == 0) carry_sh = 0;
-        __syncthreads();
-        for (uint32_t i0 = 0; i0 < ntiles; i0 += 1024) {
-            uint32_t i = i0 + threadIdx.x;
-            uint64_t v = i < ntiles ? t[i] : 0;
-            uint64_t x = v;
-            for (int o = 1; o < 32; o <<= 1) {
-                uint64_t y = __shfl_up_sync(KP_FULL, x, o);
-                if (lane_id() >= (uint32_t)o) x += y;
-            }
-            if (lane_id() == 31) wsum[threadIdx.x >> 5] = x;
-            __syncthreads();
-            if (threadIdx.x < 32) {
-                uint64_t w = wsum[threadIdx.x];
-                for (int o = 1; o < 32; o <<= 1) {
-                    uint64_t y = __shfl_up_sync(KP_FULL, w, o);
-                    if (lane_id() >= (uint32_t)o) w += y;
-                }
-                wsum[threadIdx.x] = w;  // inclusive over warps
-            }
-            __syncthreads();
-            uint64_t warp_off = (threadIdx.x >> 5) ? wsum[(threadIdx.x >> 5) - 1] : 0;
-            uint64_t carry = carry_sh;
-            if (i < ntiles) t[i] = carry + warp_off + x - v;
-            __syncthreads();
-            if (threadIdx.x == 1023) carry_sh = carry + warp_off + x;
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) {
-            uint64_t tot = carry_sh;
-            if (arr == 0) {
-                out_a[n] = (uint32_t)tot;
-                if (total_a) *total_a = tot;
-            } else {
-                out_b[n] = (uint32_t)tot;
-                if (total_b) *total_b = tot;
-            }
-        }
-        __syncthreads();
-    }
-}
-
-template <bool TWO>
-__global__ void __launch_bounds__(SCAN_THREADS) kp_scan_apply(const uint32_t* __restrict__ a,
-                                                              const uint32_t* __restrict__ b, uint32_t n,
-                                                              const uint64_t* __restrict__ tmp, uint32_t ntiles,
-                                                              uint32_t* __restrict__ out_a, uint32_t* __restrict__ out_b) {
+__global__ void __launch_bounds__(SCAN_THREADS) kp_scan_onepass(const uint32_t* __restrict__ a,
+                                                                const uint32_t* __restrict__ b, uint32_t n,
+                                                                uint32_t* __restrict__ out_a, uint32_t* __restrict__ out_b,
+                                                                uint64_t* __restrict__ tmp, uint32_t ntiles,
+                                                                uint64_t* __restrict__ total_a,
+                                                                uint64_t* __restrict__ total_b) {
     __shared__ uint32_t wsa[SCAN_THREADS / 32], wsb[SCAN_THREADS / 32];
-    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    __shared__ uint32_t sh_tile;
+    __shared__ uint64_t sh_ea, sh_eb;
+    unsigned long long* state_a = (unsigned long long*)tmp;
+    unsigned long long* state_b = state_a + ntiles;
+    if (threadIdx.x == 0) sh_tile = atomicAdd((uint32_t*)(tmp + 2 * (size_t)ntiles), 1u);
+    __syncthreads();
+    const uint32_t tile = sh_tile;
+    const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     uint32_t va[SCAN_ITEMS], vb[SCAN_ITEMS];
     uint32_t sa = 0, sb = 0;
     const bool full = base + SCAN_ITEMS <= n;     // 32 contiguous, 32-byte aligned bytes per thread
@@ -156,7 +101,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) kp_scan_apply(const uint32_t* __
     }
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
-        uint32_t i = base + k;
+        const uint32_t i = base + k;
         if (!full) {
             va[k] = i < n ? a[i] : 0;
             if (TWO) vb[k] = i < n ? b[i] : 0;
@@ -166,8 +111,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) kp_scan_apply(const uint32_t* __
     }
     uint32_t xa = sa, xb = sb;
     for (int o = 1; o < 32; o <<= 1) {
-        uint32_t ya = __shfl_up_sync(KP_FULL, xa, o);
-        uint32_t yb = __shfl_up_sync(KP_FULL, xb, o);
+        const uint32_t ya = __shfl_up_sync(KP_FULL, xa, o);
+        const uint32_t yb = __shfl_up_sync(KP_FULL, xb, o);
         if (lane_id() >= (uint32_t)o) {
             xa += ya;
             xb += yb;
@@ -178,7 +123,29 @@ __global__ void __launch_bounds__(SCAN_THREADS) kp_scan_apply(const uint32_t* __
         wsb[threadIdx.x >> 5] = xb;
     }
     __syncthreads();
-    uint32_t oa = (uint32_t)tmp[blockIdx.x], ob = TWO ? (uint32_t)tmp[ntiles + blockIdx.x] : 0;
+    if (threadIdx.x < 32) {
+        uint64_t agg_a = 0, agg_b = 0;
+        for (int w = 0; w < SCAN_THREADS / 32; w++) {
+            agg_a += wsa[w];
+            agg_b += wsb[w];
+        }
+        const uint64_t ea = kp_scan_lookback(state_a, tile, agg_a);
+        const uint64_t eb = TWO ? kp_scan_lookback(state_b, tile, agg_b) : 0ull;
+        if (threadIdx.x == 0) {
+            sh_ea = ea;
+            sh_eb = eb;
+            if (tile == ntiles - 1) {              // the last tile holds the end of the array: totals out
+                out_a[n] = (uint32_t)(ea + agg_a);
+                if (total_a) *total_a = ea + agg_a;
+                if (TWO) {
+                    out_b[n] = (uint32_t)(eb + agg_b);
+                    if (total_b) *total_b = eb + agg_b;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t oa = (uint32_t)sh_ea, ob = TWO ? (uint32_t)sh_eb : 0;
     for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) {
         oa += wsa[w];
         ob += wsb[w];
@@ -205,7 +172,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) kp_scan_apply(const uint32_t* __
     } else {
 #pragma unroll
         for (int k = 0; k < SCAN_ITEMS; k++) {
-            uint32_t i = base + k;
+            const uint32_t i = base + k;
             if (i < n) {
                 out_a[i] = ra[k];
                 if (TWO) out_b[i] = rb[k];
@@ -219,11 +186,10 @@ static int kp_scan_impl(const uint32_t* a, const uint32_t* b, uint32_t* oa, uint
                         uint64_t* ta, uint64_t* tb, cudaStream_t st) {
     uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (ntiles == 0) ntiles = 1;   // n == 0: still writes out[0] = 0 and the totals
-    kp_scan_tile_sums<TWO><<<ntiles, SCAN_THREADS, 0, st>>>(a, b, n, tmp, ntiles);
-    kp_scan_partials<TWO><<<1, 1024, 0, st>>>(tmp, ntiles, oa, ob, n, ta, tb);
-    kp_scan_apply<TWO><<<ntiles, SCAN_THREADS, 0, st>>>(a, b, n, tmp, ntiles, oa, ob);
+    cudaMemsetAsync(tmp, 0, sizeof(uint64_t) * (2 * (size_t)ntiles + 1), st);   // tile states + ticket
+    kp_scan_onepass<TWO><<<ntiles, SCAN_THREADS, 0, st>>>(a, b, n, oa, ob, tmp, ntiles, ta, tb);
     int rc = kp_launch_check("kp_scan");
-    return rc < 0 ? rc : 3;
+    return rc < 0 ? rc : 1;
 }
 
 int kp_launch_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint64_t* tmp, uint64_t* total, cudaStream_t st) {
@@ -241,6 +207,7 @@ int kp_launch_scan2(const uint32_t* a, const uint32_t* b, uint32_t* oa, uint32_t
 #define KP_PREP_THREADS 256
 #endif
 constexpr int PREP_THREADS = KP_PREP_THREADS;
+constexpr uint32_t LEN_BINS = 4096;    // counting-sort bins of the Viterbi work order (sentence length in chars)
 
 __device__ __forceinline__ bool is_cont(uint32_t c) { return (c & 0xC0u) == 0x80u; }
 __device__ __forceinline__ uint32_t lead_len(uint32_t c) {  // 0 = not a valid lead byte
@@ -255,7 +222,7 @@ __device__ __forceinline__ uint32_t lead_len(uint32_t c) {  // 0 = not a valid l
 __global__ void __launch_bounds__(PREP_THREADS) kp_prep_count(const uint8_t* __restrict__ text,
                                                               const uint64_t* __restrict__ off, uint64_t base,
                                                               uint32_t S, uint32_t B, uint32_t* __restrict__ nchar,
-                                                              uint32_t* __restrict__ err) {
+                                                              uint32_t* __restrict__ err, uint32_t* __restrict__ lenhist) {
     uint32_t s = (blockIdx.x * PREP_THREADS + threadIdx.x) >> 5;
     if (s >= S) return;
     uint64_t lo64 = off[s] - base, hi64 = off[s + 1] - base;
@@ -263,6 +230,7 @@ __global__ void __launch_bounds__(PREP_THREADS) kp_prep_count(const uint8_t* __r
         if (lane_id() == 0) {
             atomicOr(&err[1], 1u);
             nchar[s] = 0;
+            atomicAdd(&lenhist[0], 1u);
         }
         return;
     }
@@ -297,20 +265,26 @@ __global__ void __launch_bounds__(PREP_THREADS) kp_prep_count(const uint8_t* __r
     if (__reduce_add_sync(KP_FULL, conts) != __reduce_add_sync(KP_FULL, claimed)) bad = true;
     cnt = __reduce_add_sync(KP_FULL, cnt);
     if (__any_sync(KP_FULL, bad) && lane_id() == 0) atomicOr(&err[0], 1u);
-    if (lane_id() == 0) nchar[s] = cnt;
+    if (lane_id() == 0) {
+        nchar[s] = cnt;
+        atomicAdd(&lenhist[min(cnt, LEN_BINS - 1)], 1u);   // length histogram of the Viterbi work order
+    }
 }
 
 __global__ void __launch_bounds__(PREP_THREADS) kp_prep_fill(const uint8_t* __restrict__ text,
                                                              const uint64_t* __restrict__ off, uint64_t base, uint32_t S,
                                                              const uint32_t* __restrict__ coff, kp_ddict d,
                                                              uint4* __restrict__ binfo, uint32_t* __restrict__ bcount,
-                                                             uint32_t* __restrict__ ucount) {
+                                                             uint32_t* __restrict__ ucount, uint32_t* __restrict__ cursor,
+                                                             uint32_t* __restrict__ order) {
     uint32_t s = (blockIdx.x * PREP_THREADS + threadIdx.x) >> 5;
     if (s >= S) return;
     const uint32_t lane = lane_id();
     const uint32_t lo = (uint32_t)(off[s] - base), hi = (uint32_t)(off[s + 1] - base);
     const uint32_t bb = coff[s] + s;              // first boundary of this sentence
     const uint32_t n = coff[s + 1] - coff[s];     // chars
+    if (lane == 0)                                // counting-sort scatter of the Viterbi work order (cursor = scanned histogram)
+        order[atomicAdd(&cursor[min(n, LEN_BINS - 1)], 1u)] = s;
     // forward: byte offset + class of every char (Lattice::build's chars().enumerate(), lattice.rs:105)
     uint32_t run = 0;
     for (uint32_t i0 = lo; i0 < hi; i0 += 32) {
@@ -362,14 +336,15 @@ __global__ void __launch_bounds__(PREP_THREADS) kp_prep_fill(const uint8_t* __re
 int kp_launch_prep_count(const kp_chunk& c, cudaStream_t st) {
     if (c.S == 0) return 0;
     uint32_t blocks = (uint32_t)(((uint64_t)c.S * 32 + PREP_THREADS - 1) / PREP_THREADS);
-    kp_prep_count<<<blocks, PREP_THREADS, 0, st>>>(c.text, c.off, c.base, c.S, c.B, c.nchar, c.err);
+    kp_prep_count<<<blocks, PREP_THREADS, 0, st>>>(c.text, c.off, c.base, c.S, c.B, c.nchar, c.err, c.lenhist);
     return kp_launch_check("kp_prep_count");
 }
 
 int kp_launch_prep_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
     if (c.S == 0) return 0;
     uint32_t blocks = (uint32_t)(((uint64_t)c.S * 32 + PREP_THREADS - 1) / PREP_THREADS);
-    kp_prep_fill<<<blocks, PREP_THREADS, 0, st>>>(c.text, c.off, c.base, c.S, c.coff, d, c.binfo, c.bcount, c.ucount);
+    kp_prep_fill<<<blocks, PREP_THREADS, 0, st>>>(c.text, c.off, c.base, c.S, c.coff, d, c.binfo, c.bcount, c.ucount,
+                                                  c.lenhist, c.order);
     return kp_launch_check("kp_prep_fill");
 }
 
@@ -940,17 +915,10 @@ int kp_launch_bucketize(const kp_chunk& c, const kp_ddict& d, const kp_perm& pm,
 constexpr int VIT_UNROLL = KP_VIT_UNROLL;     // pairs per batch of the inner loop
 constexpr int VIT_GROUP = KP_VIT_GROUP;
 constexpr int VIT_THREADS = 128;
-constexpr uint32_t LEN_BINS = 4096;
 
 // Sentences sorted by length, longest first (counting sort on min(chars, LEN_BINS-1)): the four
 // sentences a warp steps together then have (nearly) the same number of boundaries, and the long
 // ones start first.  Order among equal lengths is arbitrary; results do not depend on it.
-__global__ void __launch_bounds__(256) kp_len_hist(uint32_t S, const uint32_t* __restrict__ coff,
-                                                   uint32_t* __restrict__ hist) {
-    uint32_t s = blockIdx.x * 256 + threadIdx.x;
-    if (s < S) atomicAdd(&hist[min(coff[s + 1] - coff[s], LEN_BINS - 1)], 1u);
-}
-
 __global__ void __launch_bounds__(1024) kp_len_scan(uint32_t* __restrict__ hist) {   // in place: bin -> first slot
     __shared__ uint32_t wsum[32];
     // 4 bins per thread, bins visited from the longest to the shortest
@@ -982,22 +950,14 @@ __global__ void __launch_bounds__(1024) kp_len_scan(uint32_t* __restrict__ hist)
     }
 }
 
-__global__ void __launch_bounds__(256) kp_len_scatter(uint32_t S, const uint32_t* __restrict__ coff,
-                                                      uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
-    uint32_t s = blockIdx.x * 256 + threadIdx.x;
-    if (s < S) order[atomicAdd(&cursor[min(coff[s + 1] - coff[s], LEN_BINS - 1)], 1u)] = s;
-}
-
 uint32_t kp_len_bins() { return LEN_BINS; }
 
+// Work order of the Viterbi sweep: kp_prep_count has filled the length histogram; this scans it into
+// first slots, and kp_prep_fill scatters the sentences through them.
 int kp_launch_length_order(const kp_chunk& c, cudaStream_t st) {
     if (c.S == 0) return 0;
-    cudaMemsetAsync(c.lenhist, 0, sizeof(uint32_t) * LEN_BINS, st);
-    kp_len_hist<<<(c.S + 255) / 256, 256, 0, st>>>(c.S, c.coff, c.lenhist);
     kp_len_scan<<<1, 1024, 0, st>>>(c.lenhist);
-    kp_len_scatter<<<(c.S + 255) / 256, 256, 0, st>>>(c.S, c.coff, c.lenhist, c.order);
-    int rc = kp_launch_check("kp_length_order");
-    return rc < 0 ? rc : 3;
+    return kp_launch_check("kp_len_scan");
 }
 
 // &base[i] of an int16 array, computed once and kept: `volatile` stops the compiler from recomputing
@@ -1269,6 +1229,11 @@ __global__ void __launch_bounds__(BT_THREADS) kp_backtrace_find(uint32_t S, cons
     if (l == 0) tcount[s] = cnt;
 }
 
+// Tokens front to back: a whole warp per sentence (~30 tokens: one round), each lane one token.
+#ifndef KP_EMIT_GROUP
+#define KP_EMIT_GROUP 32
+#endif
+constexpr int EMIT_GROUP = KP_EMIT_GROUP;
 __global__ void __launch_bounds__(BT_THREADS) kp_backtrace_emit(uint32_t S, const uint32_t* __restrict__ coff,
                                                                 const uint4* __restrict__ rec,
                                                                 const uint4* __restrict__ binfo,
@@ -1276,15 +1241,15 @@ __global__ void __launch_bounds__(BT_THREADS) kp_backtrace_emit(uint32_t S, cons
                                                                 const uint32_t* __restrict__ toff, uint64_t tok_base,
                                                                 uint64_t* __restrict__ tok_off,
                                                                 kp_token* __restrict__ tokens) {
-    const uint32_t s = (blockIdx.x * BT_THREADS + threadIdx.x) / BT_GROUP;
-    const uint32_t l = threadIdx.x & (BT_GROUP - 1);
+    const uint32_t s = (blockIdx.x * BT_THREADS + threadIdx.x) / EMIT_GROUP;
+    const uint32_t l = threadIdx.x & (EMIT_GROUP - 1);
     if (s > S) return;
     if (l == 0) tok_off[s] = tok_base + toff[s];
     if (s == S) return;
     const uint32_t bb = coff[s] + s;
     const uint32_t sent_byte0 = binfo[bb].x;     // for n == 0 this is the EOS boundary: also the sentence start
     const uint32_t w0 = toff[s], cnt = toff[s + 1] - w0;
-    for (uint32_t k = l; k < cnt; k += BT_GROUP) {
+    for (uint32_t k = l; k < cnt; k += EMIT_GROUP) {
         const uint4 r = rec[path[bb + cnt - 1 - k]];
         const uint32_t kind = r.x >> KP_KIND_SHIFT;
         kp_token t;
@@ -1306,7 +1271,7 @@ int kp_launch_backtrace_count(const kp_chunk& c, const kp_ddict& d, cudaStream_t
 }
 
 int kp_launch_backtrace_write(const kp_chunk& c, uint64_t tok_base, cudaStream_t st) {
-    kp_backtrace_emit<<<(uint32_t)(((uint64_t)(c.S + 1) * BT_GROUP + BT_THREADS - 1) / BT_THREADS), BT_THREADS, 0, st>>>(c.S, c.coff, c.rec, c.binfo, c.path, c.toff32, tok_base,
+    kp_backtrace_emit<<<(uint32_t)(((uint64_t)(c.S + 1) * EMIT_GROUP + BT_THREADS - 1) / BT_THREADS), BT_THREADS, 0, st>>>(c.S, c.coff, c.rec, c.binfo, c.path, c.toff32, tok_base,
                                                              c.tok_off, c.tokens);
     return kp_launch_check("kp_backtrace_emit");
 }

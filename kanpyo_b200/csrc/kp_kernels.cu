@@ -904,7 +904,7 @@ int kp_launch_bucketize(const kp_chunk& c, const kp_ddict& d, const kp_perm& pm,
 // Viterbi work order
 // =================================================================================================
 #ifndef KP_VIT_GROUP
-#define KP_VIT_GROUP 8
+#define KP_VIT_GROUP 0         // lanes per sentence in the sweep; 0 = chosen per batch (kp_launch_viterbi)
 #endif
 #ifndef KP_VIT_MINB
 #define KP_VIT_MINB 10
@@ -913,7 +913,6 @@ int kp_launch_bucketize(const kp_chunk& c, const kp_ddict& d, const kp_perm& pm,
 #define KP_VIT_UNROLL 4
 #endif
 constexpr int VIT_UNROLL = KP_VIT_UNROLL;     // pairs per batch of the inner loop
-constexpr int VIT_GROUP = KP_VIT_GROUP;
 constexpr int VIT_THREADS = 128;
 
 // Sentences sorted by length, longest first (counting sort on min(chars, LEN_BINS-1)): the four
@@ -1001,12 +1000,13 @@ __device__ __forceinline__ int ld_conn(const char* p) {
 // pair loop so its latency hides behind it.  The __syncwarp orders those stores before the next
 // boundary's loads.
 // =================================================================================================
+template <int GROUP>
 __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
     uint32_t S, const uint32_t* __restrict__ order, const uint32_t* __restrict__ coff, const uint32_t* __restrict__ noff,
     const uint2* __restrict__ rbk, const uint2* __restrict__ tgt, int2* red,
     int32_t* __restrict__ ndp, int32_t* __restrict__ eos_cost, const int16_t* __restrict__ connT) {
-    const uint32_t slot = (blockIdx.x * VIT_THREADS + threadIdx.x) / VIT_GROUP;
-    const uint32_t l = threadIdx.x & (VIT_GROUP - 1);
+    const uint32_t slot = (blockIdx.x * VIT_THREADS + threadIdx.x) / GROUP;
+    const uint32_t l = threadIdx.x & (GROUP - 1);
     const bool has = slot < S;
     uint32_t s = 0, bb = 0, n = 0;
     if (has) {
@@ -1037,7 +1037,7 @@ __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
         }
         const uint32_t T = t1 - t0;
         const uint32_t Tmax = __reduce_max_sync(KP_FULL, T), Rmax = __reduce_max_sync(KP_FULL, R);
-        for (uint32_t tc = 0; tc < Tmax; tc += VIT_GROUP) {
+        for (uint32_t tc = 0; tc < Tmax; tc += GROUP) {
             const bool tv = tc + l < T;
             uint2 tg = tgn;
             if (tc) tg = tv ? tgt[t0 + tc + l] : make_uint2(0u, KP_NONE);
@@ -1082,11 +1082,22 @@ __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
     }
 }
 
+// Lanes per sentence: 8 when the batch alone fills the machine with warps (148 SMs x 40 resident
+// warps), more when it does not -- a batch of few, long sentences (BASELINE.json configs[3]) is a few
+// thousand sequential chains, and what matters then is the length of each chain, not lane use.
+// Results do not depend on the choice.
 int kp_launch_viterbi(const kp_chunk& c, const kp_ddict& d, const kp_perm& pm, cudaStream_t st) {
     if (c.S == 0) return 0;
-    uint32_t blocks = (uint32_t)(((uint64_t)c.S * VIT_GROUP + VIT_THREADS - 1) / VIT_THREADS);
-    kp_viterbi<<<blocks, VIT_THREADS, 0, st>>>(c.S, c.order, c.coff, c.noff, c.rbk, c.tgt, c.red, c.ndp,
-                                               c.eos_cost, pm.connP);
+    const int group = KP_VIT_GROUP ? KP_VIT_GROUP : (c.S >= 24000 ? 8 : c.S >= 12000 ? 16 : 32);
+    const uint32_t blocks = (uint32_t)(((uint64_t)c.S * group + VIT_THREADS - 1) / VIT_THREADS);
+#define KP_VIT_LAUNCH(G)                                                                                          \
+    kp_viterbi<G><<<blocks, VIT_THREADS, 0, st>>>(c.S, c.order, c.coff, c.noff, c.rbk, c.tgt, c.red, c.ndp, c.eos_cost, \
+                                                  pm.connP)
+    if (group == 8) KP_VIT_LAUNCH(8);
+    else if (group == 16) KP_VIT_LAUNCH(16);
+    else if (group == 4) KP_VIT_LAUNCH(4);
+    else KP_VIT_LAUNCH(32);
+#undef KP_VIT_LAUNCH
     return kp_launch_check("kp_viterbi");
 }
 

@@ -173,6 +173,25 @@ def test_corpus_parity(gpu_tok, oracle_tok, vocab, kind, n):
     assert (c["bytes"], c["chars"], c["nodes"], c["tokens"]) == (ctr["B"], ctr["C"], ctr["N"], ctr["T"])
 
 
+@pytest.mark.parametrize("n", [13000, 26000])
+def test_batch_size_does_not_change_results(gpu_tok, oracle_tok, vocab, n):
+    """kp_launch_viterbi picks its lanes per sentence from the batch size (32 below 12 000 sentences, 16 below
+    24 000, 8 above): every choice must give the reference's tokens and costs."""
+    from kanpyo_b200 import corpus
+    text, off = corpus.synth_corpus(vocab, n, "cfg2")
+    res = gpu_tok.tokenize_batch_bytes(text, off)
+    o_off, o_tok, o_cost, _ = oracle_tok.tokenize_batch(text, off, threads=os.cpu_count() or 8)
+    assert_batch_equal(res, o_off, o_tok, o_cost)
+
+
+def test_first_character_paths(gpu_tok, oracle_tok):
+    """The trie walk starts from a first-character table (1-3 byte characters); 4-byte characters, NUL bytes
+    and characters no key starts with take its other paths (kp_dict.cu, kp_lattice_count)."""
+    sents = ["𠮷野家で𩸽を食べた", "\x00あ\x00い", "\x00", "😀😀😀", "aあ𠮷\x7f\u0080\u07ff\u0800\uffff", "\ud7ff\ue000",
+             "ヴァイオリンとヴィオラ", "ゟ", "東京都" + "\U0010ffff" + "に住む"]
+    _check_sentences(gpu_tok, oracle_tok, sents)
+
+
 def test_work_counters(gpu_tok, oracle_tok, vocab):
     """P, P_ok, E of the counting kernels equal the oracle's exact counts (the roofline's inputs)."""
     from kanpyo_b200 import corpus

@@ -176,6 +176,39 @@ def test_dict_pack_blob_is_validated(oracle_mod):
     assert b"" != L.kp_last_error()
 
 
+def test_first_character_table_in_blob(oracle_mod):
+    """kp_dict_pack appends a first-character table {state, base[state]} per code point < 0x10000: it must equal a
+    byte-by-byte walk of the double array (da.rs:155-182) from the root, with -1 where a transition fails."""
+    import struct
+    from helpers import to_product_dict
+    od = oracle_mod.load_ipadic()
+    blob = np.asarray(to_product_dict(od).pack()).tobytes()
+    hdr = struct.unpack_from("<QIIQ6Q7Q4Q", blob, 0)
+    da_len, off_da, off_first = hdr[4], hdr[10], hdr[19]
+    da = np.frombuffer(blob, dtype=np.int32, count=da_len * 2, offset=off_da).reshape(-1, 2)
+    assert np.array_equal(da, np.asarray(od.da, dtype=np.int32).reshape(-1, 2))
+    first = np.frombuffer(blob, dtype=np.int32, count=65536 * 2, offset=off_first).reshape(-1, 2)
+
+    def walk(bs):
+        prev, base, q = 1, int(da[1, 0]), 0
+        for c in bs:
+            q = base + c
+            if q < 0 or q >= da_len or da[q, 1] != prev:
+                return (-1, 0)
+            prev, base = q, int(da[q, 0])
+        return (q, base)
+
+    assert (first[0xD800:0xE000, 0] == -2).all()            # surrogates never occur in valid UTF-8
+    rng = np.random.default_rng(7)
+    cps = set(rng.integers(0, 0x10000, 3000).tolist()) | set(range(0x3040, 0x3100)) | {0, 0x7F, 0x80, 0x7FF, 0x800, 0xFFFF}
+    for cp in sorted(cps):
+        if 0xD800 <= cp < 0xE000:
+            continue
+        f = (int(first[cp, 0]), int(first[cp, 1]))
+        assert f[0] != -2, "IPADIC keys are whole UTF-8 strings: no entry needs the byte-wise path"
+        assert f == walk(chr(cp).encode("utf-8")), hex(cp)
+
+
 def test_shard_by_bytes_balances_and_covers():
     from kanpyo_b200.corpus import shard_by_bytes
     rng = np.random.default_rng(3)

@@ -3,7 +3,7 @@
     python tools/sweep.py                # every kanpyo_b200/_variants/libkanpyo_b200.*.so + the in-tree library
     python tools/sweep.py --one <path>   # (internal) one library in this process
 
-Per variant, in a fresh process: bit-exact parity against the oracle on a 6144-sentence cfg2 sample, the
+Per variant, in a fresh process: bit-exact parity against the oracle on 30 000 / 14 000 / 3 000-sentence cfg2 samples, the
 edge-case sentences and a 64-sentence cfg4 sample, then CUDA-event stage times of cfg2 (65 536 sentences)
 through kp_tokenize_batch, median of the timed passes.  One line per variant in gpurun_out/sweep.txt.
 """
@@ -35,12 +35,12 @@ def one(path, steps):
     out = {"lib": os.path.basename(path)}
     try:
         text, off = corpus.synth_corpus(v, 65536, "cfg2")
-        n = 6144
         extra = [s.encode("utf-8") for s in EDGE]
-        blob = text[:int(off[n])].tobytes() + b"".join(extra)
-        offs = np.concatenate([off[:n + 1], off[n] + np.cumsum([len(e) for e in extra], dtype=np.uint64)])
-        res = tk.tokenize_batch_bytes(blob, offs)
-        assert_batch_equal(res, *orc.tokenize_batch(blob, offs, threads=os.cpu_count())[:3])
+        for n in (30000, 14000, 3000):      # the sweep picks its lanes per sentence from the batch size
+            blob = text[:int(off[n])].tobytes() + b"".join(extra)
+            offs = np.concatenate([off[:n + 1], off[n] + np.cumsum([len(e) for e in extra], dtype=np.uint64)])
+            res = tk.tokenize_batch_bytes(blob, offs)
+            assert_batch_equal(res, *orc.tokenize_batch(blob, offs, threads=os.cpu_count())[:3])
         t4, o4 = corpus.synth_corpus(v, 64, "cfg4")
         res = tk.tokenize_batch_bytes(t4, o4)
         assert_batch_equal(res, *orc.tokenize_batch(t4, o4, threads=os.cpu_count())[:3])

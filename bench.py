@@ -371,7 +371,7 @@ def product_arm(args):
         traffic, traffic_src = None, None
         try:   # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
             with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-                tj = json.load(f)["kp_viterbi"]
+                tj = next(v for k, v in json.load(f).items() if k.startswith("kp_viterbi"))   # kp_viterbi<lanes>
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         except Exception:
             pass

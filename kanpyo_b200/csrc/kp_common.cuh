@@ -42,6 +42,7 @@ struct kp_ddict {
     const int16_t* connT;      // transposed copy: connT[right_of_previous * connT_stride + left_of_target]
     uint32_t connT_stride;     // elements per row (conn_col rounded up to 64)
     const int2* first;         // [KP_FIRST_CPS] trie state after one whole character: {state, base[state]}
+    uint32_t mid_char_keys;    // some key ends inside a UTF-8 character: probe for terminators after every byte
     const uint8_t* cat;        // code point -> class
     uint32_t n_cat;
     const kp_catinfo* catinfo; // [256]
@@ -59,7 +60,7 @@ struct kp_blob_header {
     uint64_t da_len, n_morphs, conn_row, conn_col, n_cat, n_unk_morphs;
     uint64_t off_da, off_dup, off_morphs, off_conn, off_cat, off_catinfo, off_unk_morphs;
     uint64_t reserved[4];      // [0] offset of the transposed matrix, [1] its row stride in elements,
-                               // [2] offset of the first-character table
+                               // [2] offset of the first-character table, [3] 1 = some key ends inside a character
 };
 
 struct kp_dict {

@@ -235,6 +235,40 @@ static int kp_pack(const kp_dict_arrays* a, std::string* blob) {
             t[2 * cp + 1] = stbase;
         }
     }
+    {
+        // Do all keys end on a character boundary?  The reference builds its trie from `String`s, so yes
+        // for any dictionary it can produce; then a terminator probe (da.rs:165-174) in the middle of a
+        // character of (valid UTF-8) input can never hit, and the counting walk skips it.  Checked here
+        // for the arrays actually given: for every leaf (base < 0, reached as base[p] + 0 from p =
+        // check[leaf]) the bytes on the way up from p must end with a whole character -- an ASCII byte,
+        // or k continuation bytes under a lead byte announcing k.  Otherwise reserved[3] = 1 and the
+        // walk probes after every byte, as the reference does.
+        const int32_t* da = a->da;
+        const uint64_t n = a->da_len;
+        bool mid = false;
+        for (uint64_t q = 0; q < n && !mid; q++) {
+            const int64_t p0 = da[2 * q + 1];
+            if (da[2 * q] >= 0 || p0 < 0 || (uint64_t)p0 >= n || da[2 * p0] != (int32_t)q) continue;   // not a terminator
+            int64_t st = p0;
+            int conts = 0;
+            while (true) {                           // byte that led to `st`: st - base[check[st]]
+                if (st == KP_ROOT_ID) { mid = conts != 0; break; }              // empty key / stray continuations
+                const int64_t par = da[2 * st + 1];
+                if (par < 0 || (uint64_t)par >= n) { mid = true; break; }
+                const int64_t c = st - da[2 * par];
+                if (c < 0 || c > 255) { mid = true; break; }
+                if ((c & 0xC0) == 0x80) {
+                    if (++conts > 3) { mid = true; break; }
+                    st = par;
+                    continue;
+                }
+                const int need = c < 0x80 ? 0 : c >= 0xF0 ? 3 : c >= 0xE0 ? 2 : c >= 0xC0 ? 1 : -1;
+                mid = need != conts;
+                break;
+            }
+        }
+        ((kp_blob_header*)p)->reserved[3] = mid ? 1 : 0;
+    }
     memcpy(p + h.off_cat, a->char_category, a->n_char_category);
     memcpy(p + h.off_catinfo, ci.data(), 256 * sizeof(kp_catinfo));
     pack_morphs(p + h.off_unk_morphs, a->unk_morphs, a->n_unk_morphs);
@@ -270,6 +304,7 @@ int kp_view_from_blob(const kp_blob_header* h, const void* d_blob, kp_ddict* v) 
     v->connT = (const int16_t*)(p + h->reserved[0]);
     v->connT_stride = (uint32_t)h->reserved[1];
     v->first = (const int2*)(p + h->reserved[2]);
+    v->mid_char_keys = h->reserved[3] != 0;
     v->cat = (const uint8_t*)(p + h->off_cat);
     v->n_cat = (uint32_t)h->n_cat;
     v->catinfo = (const kp_catinfo*)(p + h->off_catinfo);

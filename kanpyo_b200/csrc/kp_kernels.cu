@@ -365,6 +365,9 @@ constexpr uint32_t LAT_HITS = 4;   // trie hits per start boundary remembered fr
 #ifndef KP_WALK_T1
 #define KP_WALK_T1 1
 #endif
+#ifndef KP_WALK_SKIP_MID
+#define KP_WALK_SKIP_MID 1
+#endif
 #ifndef KP_CNT_MINB
 #define KP_CNT_MINB 8
 #endif
@@ -607,7 +610,9 @@ __global__ void __launch_bounds__(LAT_THREADS, KP_CNT_MINB) kp_lattice_count(
             const int ahead = nq.x;                                          // + TERMINATOR (0), da.rs:165
             const int q2 = nq.x + (c1 & 0xFF);
             const uint32_t i2 = i + 1;
-            const bool pa = (uint32_t)ahead < d.da_len;
+            // a key can only end where a character ends (kp_dict.cu checks the dictionary): no probe while
+            // the next byte is a continuation byte
+            const bool pa = (uint32_t)ahead < d.da_len && (!KP_WALK_SKIP_MID || c1 >= -64 || d.mid_char_keys);
             const bool p2 = i2 < send && (uint32_t)q2 < d.da_len;
             int2 na = make_int2(0, 0), nq2 = make_int2(0, 0);
             if (pa) na = d.da[ahead];

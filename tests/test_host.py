@@ -209,6 +209,25 @@ def test_first_character_table_in_blob(oracle_mod):
         assert f == walk(chr(cp).encode("utf-8")), hex(cp)
 
 
+def test_blob_flags_keys_ending_inside_a_character(oracle_mod):
+    """The counting walk skips terminator probes in the middle of a character when every key of the dictionary
+    ends on a character boundary (true for anything the reference can build: its keywords are Strings).
+    kp_dict_pack checks the arrays it is given and records the answer in the blob header."""
+    import struct
+    from kanpyo_b200 import builder
+
+    def flag(d):
+        return struct.unpack_from("<QIIQ6Q7Q4Q", np.asarray(d.pack()).tobytes(), 0)[20]
+
+    assert flag(to_product_dict(oracle_mod.load_ipadic())) == 0
+    d = to_product_dict(reference_fixture_dict(oracle_mod))
+    assert flag(d) == 0
+    d.da = builder.da_build(["テスト".encode(), "形".encode()[:2], "辞書".encode()], [1, 2, 3])   # a key cut inside 形
+    assert flag(d) == 1
+    d.da = builder.da_build([b"a", "あa".encode(), "\U0001f600".encode()], [1, 2, 3])
+    assert flag(d) == 0
+
+
 def test_shard_by_bytes_balances_and_covers():
     from kanpyo_b200.corpus import shard_by_bytes
     rng = np.random.default_rng(3)

@@ -354,7 +354,7 @@ int kp_launch_prep_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
 // writes the node records in the reference's insertion order.
 // =================================================================================================
 #ifndef KP_LAT_THREADS
-#define KP_LAT_THREADS 256
+#define KP_LAT_THREADS 64     // small blocks: walk lengths are heavy-tailed, a block lives as long as its longest walk
 #endif
 constexpr int LAT_THREADS = KP_LAT_THREADS;
 
@@ -369,10 +369,10 @@ constexpr uint32_t LAT_HITS = 4;   // trie hits per start boundary remembered fr
 #define KP_WALK_SKIP_MID 1
 #endif
 #ifndef KP_CNT_MINB
-#define KP_CNT_MINB 8
+#define KP_CNT_MINB 32
 #endif
 #ifndef KP_FILL_MINB
-#define KP_FILL_MINB 5
+#define KP_FILL_MINB 20
 #endif
 
 // A remembered hit is {id, chars | (duplicates << 16)}: the fill pass needs neither the trie nor `dup`.
@@ -918,7 +918,10 @@ int kp_launch_bucketize(const kp_chunk& c, const kp_ddict& d, const kp_perm& pm,
 #define KP_VIT_UNROLL 4
 #endif
 constexpr int VIT_UNROLL = KP_VIT_UNROLL;     // pairs per batch of the inner loop
-constexpr int VIT_THREADS = 128;
+#ifndef KP_VIT_THREADS
+#define KP_VIT_THREADS 128
+#endif
+constexpr int VIT_THREADS = KP_VIT_THREADS;
 
 // Sentences sorted by length, longest first (counting sort on min(chars, LEN_BINS-1)): the four
 // sentences a warp steps together then have (nearly) the same number of boundaries, and the long
@@ -1172,7 +1175,10 @@ int kp_launch_pair_count(const kp_chunk& c, cudaStream_t st) {
 // reference's strict '<' update keeps.  The path (node indices, back to front) is parked in `path`;
 // pass 2 (after the scan of the path lengths) writes the tokens front to back.
 // =================================================================================================
-constexpr int BT_THREADS = 128;
+#ifndef KP_BT_THREADS
+#define KP_BT_THREADS 128
+#endif
+constexpr int BT_THREADS = KP_BT_THREADS;
 #ifndef KP_BT_GROUP
 #define KP_BT_GROUP 8
 #endif

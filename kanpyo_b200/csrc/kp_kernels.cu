@@ -359,9 +359,6 @@ int kp_launch_prep_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
 constexpr int LAT_THREADS = KP_LAT_THREADS;
 
 constexpr uint32_t LAT_HITS = 4;   // trie hits per start boundary remembered from the counting walk
-#ifndef KP_FILL_FLAT
-#define KP_FILL_FLAT 1
-#endif
 #ifndef KP_WALK_T1
 #define KP_WALK_T1 1
 #endif
@@ -458,28 +455,19 @@ __global__ void __launch_bounds__(LAT_THREADS, FILL ? KP_FILL_MINB : KP_CNT_MINB
             // replays them and walks the trie again only for the few boundaries with more hits than that.
             uint32_t nh = FILL ? nhit[b] : 0;
             uint4 h01 = make_uint4(0, 0, 0, 0), h23 = make_uint4(0, 0, 0, 0);
-            if (FILL && KP_FILL_FLAT) h01 = hits[2 * (size_t)b];   // not waiting for nh (unused when nh == 0)
+            if (FILL) h01 = hits[2 * (size_t)b];   // not waiting for nh (unused when nh == 0)
             if (FILL && nh <= LAT_HITS) {
-                if (KP_FILL_FLAT) {
-                    if (nh > 2) h23 = hits[2 * (size_t)b + 1];
-                    // first morph of every hit: four independent gathers in flight together
-                    const uint2 z = make_uint2(0u, 0u);
-                    const uint2 m0 = nh > 0 ? ld_morph(d.morphs, h01.x - 1) : z;
-                    const uint2 m1 = nh > 1 ? ld_morph(d.morphs, h01.z - 1) : z;
-                    const uint2 m2 = nh > 2 ? ld_morph(d.morphs, h23.x - 1) : z;
-                    const uint2 m3 = nh > 3 ? ld_morph(d.morphs, h23.z - 1) : z;
-                    if (nh > 0) expand_known(h01.x, h01.y, m0);
-                    if (nh > 1) expand_known(h01.z, h01.w, m1);
-                    if (nh > 2) expand_known(h23.x, h23.y, m2);
-                    if (nh > 3) expand_known(h23.z, h23.w, m3);
-                } else {
-                    if (nh > 0) h01 = hits[2 * (size_t)b];
-                    if (nh > 2) h23 = hits[2 * (size_t)b + 1];
-                    if (nh > 0) expand_known(h01.x, h01.y, ld_morph(d.morphs, h01.x - 1));
-                    if (nh > 1) expand_known(h01.z, h01.w, ld_morph(d.morphs, h01.z - 1));
-                    if (nh > 2) expand_known(h23.x, h23.y, ld_morph(d.morphs, h23.x - 1));
-                    if (nh > 3) expand_known(h23.z, h23.w, ld_morph(d.morphs, h23.z - 1));
-                }
+                if (nh > 2) h23 = hits[2 * (size_t)b + 1];
+                // first morph of every hit: four independent gathers in flight together
+                const uint2 z = make_uint2(0u, 0u);
+                const uint2 m0 = nh > 0 ? ld_morph(d.morphs, h01.x - 1) : z;
+                const uint2 m1 = nh > 1 ? ld_morph(d.morphs, h01.z - 1) : z;
+                const uint2 m2 = nh > 2 ? ld_morph(d.morphs, h23.x - 1) : z;
+                const uint2 m3 = nh > 3 ? ld_morph(d.morphs, h23.z - 1) : z;
+                if (nh > 0) expand_known(h01.x, h01.y, m0);
+                if (nh > 1) expand_known(h01.z, h01.w, m1);
+                if (nh > 2) expand_known(h23.x, h23.y, m2);
+                if (nh > 3) expand_known(h23.z, h23.w, m3);
             } else if (FILL) {
                 if (d.da_len > KP_ROOT_ID)
                     o = kp_fill_rewalk(text, bp, send, b, kp_trie_view{d.da, d.da_len, d.dup, d.morphs}, rec, o);
@@ -743,7 +731,7 @@ int kp_launch_column_order(const kp_chunk& c, const kp_ddict& d, const kp_perm& 
 // =================================================================================================
 // Bucketize.  One warp per sentence walks its nodes in order, 32 at a time, and builds
 //   * bnode: the reference's edges[end] lists (stable: ascending node index), used by the back-trace;
-//   * red / rcnt / tgt: the REDUCED buckets the Viterbi sweep scans (layout in kp_kernels.cuh).
+//   * red / rbk / tgt: the REDUCED buckets the Viterbi sweep scans (layout in kp_kernels.cuh).
 // Why reduced: every start position inside a same-class run emits the class's unknown nodes, and
 // they all end at the run's end -- buckets of 100+ entries that differ only in dp.  A successor only
 // ever needs min(dp) per distinct (right_id); for unknown nodes the distinct ids are known
@@ -755,9 +743,6 @@ int kp_launch_column_order(const kp_chunk& c, const kp_ddict& d, const kp_perm& 
 #define KP_SENT_THREADS 64
 #endif
 constexpr int SENT_THREADS = KP_SENT_THREADS;   // one warp per sentence
-#ifndef KP_BK_PIPE
-#define KP_BK_PIPE 1
-#endif
 #ifndef KP_BK_SMEM
 #define KP_BK_SMEM 256
 #endif
@@ -804,7 +789,6 @@ __global__ void __launch_bounds__(SENT_THREADS, KP_BK_MINB) kp_bucketize(uint32_
         for (uint32_t p = lane; p <= n; p += 32) sfill[p] = make_uint2(0u, 0u);
         __syncwarp();
     }
-#if KP_BK_PIPE
     // Software pipeline, two rounds deep: the node records of round k+2 and the gathers that depend on
     // the records of round k+1 (bucket base, and for unknown nodes the known count and first id of
     // the class) are in flight while round k does its ranking and stores.
@@ -857,44 +841,6 @@ __global__ void __launch_bounds__(SENT_THREADS, KP_BK_MINB) kp_bucketize(uint32_
         }
         __syncwarp();
     }
-#else
-    uint4 rnext = n0 + lane < n1 ? rec[n0 + lane] : make_uint4(0, 0, 0, 0);   // one round ahead
-    for (uint32_t i0 = n0; i0 < n1; i0 += 32) {
-        uint32_t i = i0 + lane;
-        bool valid = i < n1;
-        uint4 r = rnext;
-        if (i + 32 < n1) rnext = rec[i + 32];
-        uint32_t e = valid ? r.y + (r.w >> 16) : KP_NONE;   // end boundary = start + char_len (lattice.rs:187,200)
-        const bool known = valid && (r.x >> KP_KIND_SHIFT) == KP_CLASS_KNOWN;
-        uint32_t m = __match_any_sync(KP_FULL, e);
-        const uint32_t km = m & __ballot_sync(KP_FULL, known);
-        uint32_t leader = (uint32_t)__ffs(m) - 1;
-        uint2 old = make_uint2(0, 0);
-        if (valid && lane == leader) {
-            uint2* cur = insm ? &sfill[e - bb] : &bfill[e];
-            old = *cur;
-            *cur = make_uint2(old.x + (uint32_t)__popc(m), old.y + (uint32_t)__popc(km));
-        }
-        old.x = __shfl_sync(KP_FULL, old.x, leader);
-        old.y = __shfl_sync(KP_FULL, old.y, leader);
-        if (valid) {
-            const uint32_t first = e == bb ? 1u : 0u;       // BOS occupies slot 0 of the first bucket
-            const uint32_t base = boff[e];
-            bnode[base + first + old.x + (uint32_t)__popc(m & lanemask_lt())] = i;
-            uint32_t slot;
-            if (known) {
-                slot = base + first + old.y + (uint32_t)__popc(km & lanemask_lt());
-            } else {                                        // shared slot of (end boundary, unknown id)
-                const uint32_t cat = binfo[r.y].w & 0xFFu;  // class of the node's first char = of all its chars
-                slot = base + (bcount[e] - ucount[e]) + ((r.x & KP_ID_MASK) - (uint32_t)d.catinfo[cat].unk_first);
-            }
-            red[slot] = make_int2(KP_INF, (int)((r.z >> 16) * d.connT_stride));       // {dp, element offset of row right_id in connT}
-            tgt[i] = make_uint2((uint32_t)perm[r.z & 0xFFFFu] | (r.w << 16),           // left id as its column in connP
-                                known ? slot : slot | KP_SLOT_SHARED);
-        }
-        __syncwarp();
-    }
-#endif
 }
 
 int kp_launch_bucketize(const kp_chunk& c, const kp_ddict& d, const kp_perm& pm, cudaStream_t st) {

@@ -12,16 +12,19 @@
 //   ucount  u32[NB]       UNKNOWN nodes ending at each boundary (subset of bcount)
 //   bnode   u32[N]        the reference's `edges` lists: per bucket entry (ascending node index) the node
 //                         index (KP_NONE for BOS); bucket of boundary b = [boff[b], boff[b+1])
-//   red     int2[N]       REDUCED buckets, what the Viterbi sweep scans as predecessors: {min dp, byte offset of
+//   nhit    u8[NB]        trie hits the counting walk saw at each start boundary (saturating)
+//   hits    uint4[2 NB]   its first four, {id, chars | duplicates << 16} each: the fill pass replays them
+//   red     int2[N]       REDUCED buckets, what the Viterbi sweep scans as predecessors: {min dp, element offset of
 //                         row right_id in the transposed connection matrix}.
-//                         Region of boundary b = [boff[b], boff[b] + rcnt[b]): one entry per known node
+//                         Region of boundary b = rbk[b].x .. + rbk[b].y: one entry per known node
 //                         ending at b (BOS first at a sentence's first boundary), then one entry per
 //                         unknown-morph id of the class of the char before b, shared by ALL unknown nodes
 //                         with that id ending at b (they have the same right_id; only their minimum dp
 //                         can matter to a successor)
-//   rcnt    u32[NB]       entries in the reduced bucket of each boundary
+//   rbk     uint2[NB]     {boff[b], entries in the reduced bucket} of each boundary (one load per step of the sweep)
 //   tgt     uint2[N]      per node, what the sweep needs of a TARGET: {column of left_id | cost<<16, reduced slot}
-//                         (global index into red; KP_NONE for EOS)
+//                         (global index into red, | KP_SLOT_SHARED for an unknown node's shared slot;
+//                         KP_NONE for EOS)
 //   ndp     i32[N]        dp of every node (the back-trace and the lattice dump read it)
 //   path    u32[NB]       best path of each sentence, back to front, at the sentence's boundary base
 //   pre     u32[N]        (lattice dump only) predecessor as a bucket slot (KP_NONE = Option::None)

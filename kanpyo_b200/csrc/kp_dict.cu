@@ -243,29 +243,42 @@ static int kp_pack(const kp_dict_arrays* a, std::string* blob) {
         // check[leaf]) the bytes on the way up from p must end with a whole character -- an ASCII byte,
         // or k continuation bytes under a lead byte announcing k.  Otherwise reserved[3] = 1 and the
         // walk probes after every byte, as the reference does.
+        // The same walk up to the root gives the key's length: node records carry a word's length in 16
+        // bits (kp_kernels.cuh), so a key longer than 65 535 bytes is refused here rather than truncated.
         const int32_t* da = a->da;
         const uint64_t n = a->da_len;
         bool mid = false;
-        for (uint64_t q = 0; q < n && !mid; q++) {
+        for (uint64_t q = 0; q < n; q++) {
             const int64_t p0 = da[2 * q + 1];
             if (da[2 * q] >= 0 || p0 < 0 || (uint64_t)p0 >= n || da[2 * p0] != (int32_t)q) continue;   // not a terminator
             int64_t st = p0;
             int conts = 0;
-            while (true) {                           // byte that led to `st`: st - base[check[st]]
-                if (st == KP_ROOT_ID) { mid = conts != 0; break; }              // empty key / stray continuations
+            bool tail_done = false;
+            uint32_t depth = 0;
+            while (st != KP_ROOT_ID) {               // byte that led to `st`: st - base[check[st]]
                 const int64_t par = da[2 * st + 1];
-                if (par < 0 || (uint64_t)par >= n) { mid = true; break; }
-                const int64_t c = st - da[2 * par];
-                if (c < 0 || c > 255) { mid = true; break; }
-                if ((c & 0xC0) == 0x80) {
-                    if (++conts > 3) { mid = true; break; }
-                    st = par;
-                    continue;
+                if (par < 0 || (uint64_t)par >= n || ++depth > 65535) {
+                    if (depth > 65535) {
+                        kp_set_error("trie leaf %llu: key longer than 65535 bytes (or a cycle in `check`)",
+                                     (unsigned long long)q);
+                        return KP_ERR_DICT;
+                    }
+                    mid = true;                      // not reachable from the root: never matched, but do not trust it
+                    break;
                 }
-                const int need = c < 0x80 ? 0 : c >= 0xF0 ? 3 : c >= 0xE0 ? 2 : c >= 0xC0 ? 1 : -1;
-                mid = need != conts;
-                break;
+                if (!tail_done) {
+                    const int64_t c = st - da[2 * par];
+                    if (c < 0 || c > 255) { mid = true; tail_done = true; }
+                    else if ((c & 0xC0) == 0x80) { if (++conts > 3) { mid = true; tail_done = true; } }
+                    else {
+                        const int need = c < 0x80 ? 0 : c >= 0xF0 ? 3 : c >= 0xE0 ? 2 : c >= 0xC0 ? 1 : -1;
+                        if (need != conts) mid = true;
+                        tail_done = true;
+                    }
+                }
+                st = par;
             }
+            if (!tail_done && conts) mid = true;     // continuation bytes straight under the root
         }
         ((kp_blob_header*)p)->reserved[3] = mid ? 1 : 0;
     }

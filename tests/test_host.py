@@ -226,6 +226,11 @@ def test_blob_flags_keys_ending_inside_a_character(oracle_mod):
     assert flag(d) == 1
     d.da = builder.da_build([b"a", "あa".encode(), "\U0001f600".encode()], [1, 2, 3])
     assert flag(d) == 0
+    # a word's length travels in 16 bits on the device: longer keys are refused, not truncated
+    from kanpyo_b200 import _lib
+    d.da = builder.da_build([b"a" * 70000, "テスト".encode(), "辞書".encode()], [1, 2, 3])
+    with pytest.raises(_lib.KanpyoB200Error):
+        d.pack()
 
 
 def test_shard_by_bytes_balances_and_covers():

@@ -41,7 +41,7 @@ typedef enum kp_status {
     KP_ERR_DICT = -3,         /* dictionary arrays fail validation (an index the reference would panic on) */
     KP_ERR_UTF8 = -4,         /* input is not valid UTF-8 (Rust's &str guarantees validity; the ABI checks) */
     KP_ERR_NOMEM = -5,        /* host or device allocation failed */
-    KP_ERR_TOO_LARGE = -6,    /* a single chunk exceeds the 2^31-byte / 2^32-node device index range */
+    KP_ERR_TOO_LARGE = -6,    /* a single chunk exceeds the 2^31-byte / 2^31-node device index range */
     KP_ERR_BLOB = -7          /* packed dictionary blob has a bad magic / version / size */
 } kp_status;
 

@@ -860,6 +860,12 @@ int kp_launch_bucketize(const kp_chunk& c, const kp_ddict& d, const kp_perm& pm,
 #ifndef KP_VIT_MINB
 #define KP_VIT_MINB 10
 #endif
+#ifndef KP_VIT_LATEPF
+#define KP_VIT_LATEPF 1         // next boundary's bounds / targets issued just before the pair loop (see kp_viterbi)
+#endif
+#ifndef KP_VIT_TGEARLY
+#define KP_VIT_TGEARLY 1        // next boundary's first targets fetched a whole step ahead
+#endif
 #ifndef KP_VIT_UNROLL
 #define KP_VIT_UNROLL 4
 #endif
@@ -956,7 +962,7 @@ __device__ __forceinline__ int ld_conn(const char* p) {
 // =================================================================================================
 template <int GROUP>
 __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
-    uint32_t S, const uint32_t* __restrict__ order, const uint32_t* __restrict__ coff, const uint32_t* __restrict__ noff,
+    uint32_t S, uint32_t N, const uint32_t* __restrict__ order, const uint32_t* __restrict__ coff, const uint32_t* __restrict__ noff,
     const uint2* __restrict__ rbk, const uint2* __restrict__ tgt, int2* red,
     int32_t* __restrict__ ndp, int32_t* __restrict__ eos_cost, const int16_t* __restrict__ connT) {
     const uint32_t slot = (blockIdx.x * VIT_THREADS + threadIdx.x) / GROUP;
@@ -985,12 +991,31 @@ __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
         const bool act = has && p <= n;
         const uint32_t t1 = act ? t1n : t0, R = act ? bkn.y : 0u;
         const int2* const rbase = red + bkn.x;
-        if (has && p < n) {                       // bounds of the next boundary, off the critical path
-            t1n = noff[bb + p + 2];
-            bkn = rbk[bb + p + 1];
-        }
+#if KP_VIT_TGEARLY
+        uint2 tnx = make_uint2(0u, KP_NONE);      // next boundary's first targets, fetched a whole step ahead
+#endif
+        // Bounds (and first targets) of the next boundary.  Issued just before the pair loop rather than
+        // here: ptxas puts these loads on the scoreboard of the merge-value load, and the first wait on
+        // that scoreboard would otherwise come a few instructions later, exposing their whole latency.
+        auto fetch_next = [&]() {
+            if (has && p < n) {
+                t1n = noff[bb + p + 2];
+                bkn = rbk[bb + p + 1];
+#if KP_VIT_TGEARLY
+                // the address is known now, whether the lane has a target there only once t1n arrives:
+                // fetch anyway (clamped to the array), decide at the end of the step
+                tnx = tgt[min(t1 + l, N)];
+#endif
+            }
+        };
+#if !KP_VIT_LATEPF
+        fetch_next();
+#endif
         const uint32_t T = t1 - t0;
         const uint32_t Tmax = __reduce_max_sync(KP_FULL, T), Rmax = __reduce_max_sync(KP_FULL, R);
+#if KP_VIT_LATEPF
+        if (Tmax == 0) fetch_next();              // no node starts here in any of the warp's sentences
+#endif
         for (uint32_t tc = 0; tc < Tmax; tc += GROUP) {
             const bool tv = tc + l < T;
             uint2 tg = tgn;
@@ -1001,6 +1026,9 @@ __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
             int* const slotp = &red[tg.y & ~KP_SLOT_SHARED].x;
             int merged = KP_INF;
             if (tv && !eos && (tg.y & KP_SLOT_SHARED)) merged = *slotp;
+#if KP_VIT_LATEPF
+            if (tc == 0) fetch_next();
+#endif
             int best = INT_MAX;
             const int2* rp = rbase;
             int rem = tv ? (int)R : 0;
@@ -1030,7 +1058,11 @@ __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
             }
         }
         // the next boundary's first targets: the address does not depend on this step's results
+#if KP_VIT_TGEARLY
+        tgn = (has && p < n && t1 + l < t1n) ? tnx : make_uint2(0u, KP_NONE);
+#else
         tgn = (has && p < n && t1 + l < t1n) ? tgt[t1 + l] : make_uint2(0u, KP_NONE);
+#endif
         __syncwarp();
         t0 = t1;
     }
@@ -1045,7 +1077,7 @@ int kp_launch_viterbi(const kp_chunk& c, const kp_ddict& d, const kp_perm& pm, c
     const int group = KP_VIT_GROUP ? KP_VIT_GROUP : (c.S >= 24000 ? 8 : c.S >= 12000 ? 16 : 32);
     const uint32_t blocks = (uint32_t)(((uint64_t)c.S * group + VIT_THREADS - 1) / VIT_THREADS);
 #define KP_VIT_LAUNCH(G)                                                                                          \
-    kp_viterbi<G><<<blocks, VIT_THREADS, 0, st>>>(c.S, c.order, c.coff, c.noff, c.rbk, c.tgt, c.red, c.ndp, c.eos_cost, \
+    kp_viterbi<G><<<blocks, VIT_THREADS, 0, st>>>(c.S, c.N, c.order, c.coff, c.noff, c.rbk, c.tgt, c.red, c.ndp, c.eos_cost, \
                                                   pm.connP)
     if (group == 8) KP_VIT_LAUNCH(8);
     else if (group == 16) KP_VIT_LAUNCH(16);

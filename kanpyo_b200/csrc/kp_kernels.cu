@@ -863,6 +863,9 @@ int kp_launch_bucketize(const kp_chunk& c, const kp_ddict& d, const kp_perm& pm,
 #ifndef KP_VIT_LATEPF
 #define KP_VIT_LATEPF 1         // next boundary's bounds / targets issued just before the pair loop (see kp_viterbi)
 #endif
+#ifndef KP_VIT_TGEARLY2
+#define KP_VIT_TGEARLY2 0       // candidate for the next round: second chunk of targets a step ahead as well
+#endif
 #ifndef KP_VIT_TGEARLY
 #define KP_VIT_TGEARLY 1        // next boundary's first targets fetched a whole step ahead
 #endif
@@ -987,12 +990,19 @@ __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
     // cluster (noun / unknown-word ids are neighbours), so a group's gather touches ~2 lines, not ~5
     uint2 tgn = make_uint2(0u, KP_NONE);          // first target chunk of the next boundary, prefetched
     if (has && t0 + l < t1n) tgn = tgt[t0 + l];
+#if KP_VIT_TGEARLY2
+    uint2 tgn2 = make_uint2(0u, KP_NONE);
+    if (has && t0 + GROUP + l < t1n) tgn2 = tgt[t0 + GROUP + l];
+#endif
     for (uint32_t p = 0; p < steps; p++) {
         const bool act = has && p <= n;
         const uint32_t t1 = act ? t1n : t0, R = act ? bkn.y : 0u;
         const int2* const rbase = red + bkn.x;
 #if KP_VIT_TGEARLY
         uint2 tnx = make_uint2(0u, KP_NONE);      // next boundary's first targets, fetched a whole step ahead
+#endif
+#if KP_VIT_TGEARLY2
+        uint2 tnx2 = make_uint2(0u, KP_NONE);     // and its second chunk of targets (candidate, not yet measured)
 #endif
         // Bounds (and first targets) of the next boundary.  Issued just before the pair loop rather than
         // here: ptxas puts these loads on the scoreboard of the merge-value load, and the first wait on
@@ -1005,6 +1015,9 @@ __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
                 // the address is known now, whether the lane has a target there only once t1n arrives:
                 // fetch anyway (clamped to the array), decide at the end of the step
                 tnx = tgt[min(t1 + l, N)];
+#endif
+#if KP_VIT_TGEARLY2
+                tnx2 = tgt[min(t1 + GROUP + l, N)];
 #endif
             }
         };
@@ -1019,6 +1032,10 @@ __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
         for (uint32_t tc = 0; tc < Tmax; tc += GROUP) {
             const bool tv = tc + l < T;
             uint2 tg = tgn;
+#if KP_VIT_TGEARLY2
+            if (tc == GROUP) tg = tgn2;
+            else
+#endif
             if (tc) tg = tv ? tgt[t0 + tc + l] : make_uint2(0u, KP_NONE);
             const uint64_t crow = elem_ptr_pinned(connT, tg.x & 0xFFFFu);   // this target's column; entries carry row offsets
             // reduced slot: bit 31 marks a shared one (unknown node); KP_NONE = EOS, which ends nowhere
@@ -1058,6 +1075,9 @@ __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
             }
         }
         // the next boundary's first targets: the address does not depend on this step's results
+#if KP_VIT_TGEARLY2
+        tgn2 = (has && p < n && t1 + GROUP + l < t1n) ? tnx2 : make_uint2(0u, KP_NONE);
+#endif
 #if KP_VIT_TGEARLY
         tgn = (has && p < n && t1 + l < t1n) ? tnx : make_uint2(0u, KP_NONE);
 #else

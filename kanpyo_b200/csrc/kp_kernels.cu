@@ -349,9 +349,11 @@ int kp_launch_prep_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
 }
 
 // =================================================================================================
-// Lattice build: one thread per boundary walks the double array from that char to the end of the
-// sentence.  Pass 1 counts nodes per start boundary and per end boundary; pass 2 (after the scans)
-// writes the node records in the reference's insertion order.
+// Lattice build: one thread per boundary.  Pass 1 (kp_lattice_count below; kp_lattice_walk<false, true>
+// is the plain statement of the same walk and serves the work counters) walks the double array from
+// that char to the end of the sentence and counts nodes per start boundary and per end boundary;
+// pass 2 (kp_lattice_walk<true, false>, after the scans) writes the node records in the reference's
+// insertion order, replaying the hits pass 1 remembered.
 // =================================================================================================
 #ifndef KP_LAT_THREADS
 #define KP_LAT_THREADS 64     // small blocks: walk lengths are heavy-tailed, a block lives as long as its longest walk
@@ -544,11 +546,13 @@ __global__ void __launch_bounds__(LAT_THREADS, FILL ? KP_FILL_MINB : KP_CNT_MINB
 //   * the first character is one lookup in the first-character table (kp_dict.cu);
 //   * per further byte, the terminator probe da[base[q]] and the next transition da[base[q] + byte]
 //     are issued together (both depend only on da[q], da.rs:160-174) and the text byte is fetched a
-//     step ahead; a failed range test clears `alive` instead of loading;
+//     step ahead; a failed range test clears `alive` instead of loading; the probe is skipped in the
+//     middle of a character when every key of the dictionary ends on a character boundary;
 //   * the first LAT_HITS hits {id, chars} go to a per-thread column of shared memory (no register
 //     rotation in the loop); their duplicate counts are looked up after the walk, off its chain.
-// The kernel is issue-bound with ~7 of 32 lanes live (walk lengths are heavy-tailed), so the loop is
-// kept to as few instructions as the compiler will give.
+// ~7 of 32 lanes are live in the loop (walk lengths are heavy-tailed) and the kernel waits on its L2
+// gathers: what pays is fewer gathers per walk and small blocks (a block lives as long as its
+// longest walk).
 // =================================================================================================
 __global__ void __launch_bounds__(LAT_THREADS, KP_CNT_MINB) kp_lattice_count(
     const uint8_t* __restrict__ text, const uint4* __restrict__ binfo, uint32_t NB, kp_ddict d,
@@ -946,7 +950,7 @@ __device__ __forceinline__ int ld_conn(const char* p) {
 // =================================================================================================
 // Viterbi forward sweep (lattice.rs:116-143, dp values only).
 //
-// A warp carries 32 / VIT_GROUP sentences (taken in length order), VIT_GROUP lanes each, and steps all
+// A warp carries 32 / GROUP sentences (taken in length order), GROUP lanes each, and steps all
 // of them boundary by boundary with warp-uniform loop bounds, so the groups share every issued
 // instruction.  Lanes hold the nodes STARTING at the boundary (targets); each lane folds the
 // boundary's reduced bucket (predecessors) with one DPX add-min per pair:

@@ -364,6 +364,9 @@ constexpr uint32_t LAT_HITS = 4;   // trie hits per start boundary remembered fr
 #ifndef KP_WALK_T1
 #define KP_WALK_T1 1
 #endif
+#ifndef KP_HITS_NH
+#define KP_HITS_NH 0           // candidate for the next round (unmeasured): the hit count rides in the spare bits
+#endif                         // of the first hit record, so the fill pass reads one stream less (no nhit)
 #ifndef KP_WALK_SKIP_MID
 #define KP_WALK_SKIP_MID 1
 #endif
@@ -455,9 +458,19 @@ __global__ void __launch_bounds__(LAT_THREADS, FILL ? KP_FILL_MINB : KP_CNT_MINB
         } else {
             // The counting walk remembers its first LAT_HITS hits {id, chars | dups << 16}; the fill pass
             // replays them and walks the trie again only for the few boundaries with more hits than that.
-            uint32_t nh = FILL ? nhit[b] : 0;
             uint4 h01 = make_uint4(0, 0, 0, 0), h23 = make_uint4(0, 0, 0, 0);
+#if KP_HITS_NH
+            uint32_t nh = 0;
+            if (FILL) {                            // min(hits, 5) in the two spare bits of ids 0 and 1
+                h01 = hits[2 * (size_t)b];
+                nh = (h01.x >> 30) | ((h01.z >> 30) << 2);
+                h01.x &= KP_ID_MASK;
+                h01.z &= KP_ID_MASK;
+            }
+#else
+            uint32_t nh = FILL ? nhit[b] : 0;
             if (FILL) h01 = hits[2 * (size_t)b];   // not waiting for nh (unused when nh == 0)
+#endif
             if (FILL && nh <= LAT_HITS) {
                 if (nh > 2) h23 = hits[2 * (size_t)b + 1];
                 // first morph of every hit: four independent gathers in flight together
@@ -507,10 +520,19 @@ __global__ void __launch_bounds__(LAT_THREADS, FILL ? KP_FILL_MINB : KP_CNT_MINB
                     base = nq.x;
                 }
                 nhit[b] = (uint8_t)min(nh, 255u);
+#if KP_HITS_NH
+                h01.x |= (min(nh, 5u) & 3u) << 30;
+                h01.z |= (min(nh, 5u) >> 2) << 30;
+                hits[2 * (size_t)b] = h01;
+#else
                 if (nh > 0) hits[2 * (size_t)b] = h01;
+#endif
                 if (nh > 2) hits[2 * (size_t)b + 1] = h23;
             } else {
                 nhit[b] = 0;
+#if KP_HITS_NH
+                hits[2 * (size_t)b] = make_uint4(0, 0, 0, 0);
+#endif
             }
             const bool matched = nh > 0;
             // unknown words (lattice.rs:42-99)
@@ -648,9 +670,18 @@ __global__ void __launch_bounds__(LAT_THREADS, KP_CNT_MINB) kp_lattice_count(
                 h[u].y |= (k[u] - 1) << 16;
             }
         }
+#if KP_HITS_NH
+        h[0].x |= (min(nh, 5u) & 3u) << 30;
+        h[1].x |= (min(nh, 5u) >> 2) << 30;
+        hits[2 * (size_t)b] = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y);
+#else
         if (nh > 0) hits[2 * (size_t)b] = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y);
+#endif
         if (nh > 2) hits[2 * (size_t)b + 1] = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
     }
+#if KP_HITS_NH
+    else hits[2 * (size_t)b] = make_uint4(0, 0, 0, 0);
+#endif
     nhit[b] = (uint8_t)min(nh, 255u);
     // unknown words (lattice.rs:42-99)
     const kp_catinfo ci = d.catinfo[bi.w & 0xFFu];

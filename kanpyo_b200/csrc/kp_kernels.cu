@@ -206,6 +206,9 @@ int kp_launch_scan2(const uint32_t* a, const uint32_t* b, uint32_t* oa, uint32_t
 #ifndef KP_PREP_THREADS
 #define KP_PREP_THREADS 256
 #endif
+#ifndef KP_PREP_PF
+#define KP_PREP_PF 0           // candidate for the next round (unmeasured): next slice's text byte fetched a pass ahead
+#endif
 constexpr int PREP_THREADS = KP_PREP_THREADS;
 constexpr uint32_t LEN_BINS = 4096;    // counting-sort bins of the Viterbi work order (sentence length in chars)
 
@@ -237,8 +240,16 @@ __global__ void __launch_bounds__(PREP_THREADS) kp_prep_count(const uint8_t* __r
     uint32_t lo = (uint32_t)lo64, hi = (uint32_t)hi64;
     uint32_t cnt = 0, conts = 0, claimed = 0;
     bool bad = false;
+#if KP_PREP_PF
+    uint32_t cnext = lo + lane_id() < hi ? text[lo + lane_id()] : 0u;   // next slice's byte, one iteration ahead
+#endif
     for (uint32_t i = lo + lane_id(); i < hi; i += 32) {
+#if KP_PREP_PF
+        const uint32_t c = cnext;
+        if (i + 32 < hi) cnext = text[i + 32];
+#else
         uint32_t c = text[i];
+#endif
         if (!is_cont(c)) {
             cnt++;
             uint32_t L = lead_len(c);
@@ -287,9 +298,17 @@ __global__ void __launch_bounds__(PREP_THREADS) kp_prep_fill(const uint8_t* __re
         order[atomicAdd(&cursor[min(n, LEN_BINS - 1)], 1u)] = s;
     // forward: byte offset + class of every char (Lattice::build's chars().enumerate(), lattice.rs:105)
     uint32_t run = 0;
+#if KP_PREP_PF
+    uint32_t cnext = lo + lane < hi ? text[lo + lane] : 0x80u;           // next slice's byte, one iteration ahead
+#endif
     for (uint32_t i0 = lo; i0 < hi; i0 += 32) {
         uint32_t i = i0 + lane;
+#if KP_PREP_PF
+        const uint32_t c = cnext;
+        cnext = i + 32 < hi ? text[i + 32] : 0x80u;
+#else
         uint32_t c = i < hi ? text[i] : 0x80u;
+#endif
         bool st = !is_cont(c);
         uint32_t m = __ballot_sync(KP_FULL, st);
         if (st) {

@@ -233,6 +233,33 @@ def test_blob_flags_keys_ending_inside_a_character(oracle_mod):
         d.pack()
 
 
+def test_sass_invariants_of_the_hot_kernels():
+    """What the profiles rest on, checked on the built library without a GPU: the sweep's pair loop is one DPX
+    add-min per pair (VIADDMNMX), and neither it nor the counting walk spills registers to local memory."""
+    import shutil
+    from kanpyo_b200 import build as kbuild
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", kbuild.build()], capture_output=True, text=True).stdout
+    funcs, cur = {}, None
+    for ln in sass.splitlines():
+        if "Function :" in ln:
+            cur = ln.split("Function :")[1].strip()
+            funcs[cur] = []
+        elif cur:
+            funcs[cur].append(ln)
+    vit = [k for k in funcs if "kp_viterbi" in k]
+    assert len(vit) >= 3, vit                       # 8, 16 and 32 lanes per sentence (and 4 for sweeps)
+    for k in vit:
+        body = "\n".join(funcs[k])
+        assert "VIADDMNMX" in body, k
+        if "ILi8E" in k:
+            assert "STL" not in body and "LDL" not in body, "%s spills" % k
+    cnt = [k for k in funcs if "kp_lattice_count" in k]
+    assert cnt and all("STL" not in "\n".join(funcs[k]) for k in cnt)
+
+
 def test_shard_by_bytes_balances_and_covers():
     from kanpyo_b200.corpus import shard_by_bytes
     rng = np.random.default_rng(3)

@@ -7,16 +7,21 @@
 
 A step = one pass of the hot path (lattice build + Viterbi + back-trace, `Tokenizer::tokenize` per
 sentence) over one batch: BASELINE.json configs[1], 65 536 synthetic sentences (mean 80 chars,
-Zipf vocabulary over IPADIC) per GPU.  Weak scaling: every rank tokenizes its own 65 536-sentence
-shard of an N x 65 536-sentence batch; the dictionary reaches ranks > 0 through one NCCL broadcast;
-no collective runs inside the timed data path.
+Zipf vocabulary over IPADIC) per GPU.  The main line is weak scaling: every rank tokenizes its own
+65 536-sentence batch; the dictionary reaches ranks > 0 through one NCCL broadcast; at N > 1 every
+timed step ends with the NCCL gather of the token records on rank 0.  `strong_scaling` (N > 1) is
+BASELINE.json configs[4]: ONE 65 536-sentence batch split into byte-balanced shards, gather included.
 
   value     input bytes of all ranks / device time (CUDA events on the library's stream around the
-            whole step), text already resident in HBM; max over ranks
-  e2e       same metric through the C-ABI `kp_tokenize_batch` with pinned HOST buffers: H2D of the
-            text + offsets, kernels, D2H of the token records, wall clock around the call
-  roofline  dominant kernel (kp_viterbi): algorithmic bytes 16 N + 8 E / its
-            CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+            whole step, plus the gather's events at N > 1), text already resident in HBM; max over ranks
+  e2e       same metric through the C-ABI queue (`kp_queue_submit` / `kp_queue_wait`) with pinned HOST
+            buffers: H2D of the text + offsets, kernels, D2H of the compact token records, all inside
+            the wall clock, successive steps overlapped; `sync_call` is the blocking `kp_tokenize_batch8`
+  parity    the benched batch's result (device path, e2e path, gathered results at N > 1) compared
+            bit-for-bit with the oracle on the same bytes; a mismatch fails the run (exit code 3)
+  roofline  dominant kernel: algorithmic bytes / its CUDA-event duration, against
+            MEASURED_PEAKS.json hbm_gbs
+  latency_us  one sentence per call (`kp_tokenize`), p50 / p99, beside the CPU port's time
   cpu_baseline / --impl reference: oracle/ref_tokenize.cpp (the reference's CPU algorithm restated in
             C++, same shape: per-node heap strings, vector-of-vector buckets) on the host cores.
 """
@@ -133,6 +138,7 @@ def host_info():
 
 
 def load_dict_and_corpus(kind, n_sent, seed_offset, rank=0, world=1, barrier=None):
+    """The product's dictionary and the synthetic batch of rank `seed_offset` (seed = corpus.SEED + rank)."""
     from kanpyo_b200 import builder, corpus
     if world > 1 and rank != 0:
         barrier()                       # rank 0 builds (or loads) the cache first
@@ -227,6 +233,57 @@ def reference_arm(args):
 # ----------------------------------------------------------------------------------------------------
 # product arm
 # ----------------------------------------------------------------------------------------------------
+def oracle_reference(text, off, threads):
+    """The oracle's answer for a batch: (tok_off, tokens int64[n,6], eos_cost).  Checker only."""
+    from oracle import oracle
+    otk = oracle.OracleTokenizer(oracle.load_ipadic())
+    o_off, o_tok, o_cost, _ = otk.tokenize_batch(text, off, threads=threads)
+    return o_off, o_tok, o_cost
+
+
+def compare_with_oracle(ref, tok_off, tokens16, eos):
+    """Bit-exact comparison of a (tok_off, kp_token records, dp[EOS]) result with the oracle's."""
+    o_off, o_tok, o_cost = ref
+    if len(tok_off) != len(o_off) or not np.array_equal(np.asarray(tok_off, np.uint64), o_off):
+        return "token offsets differ"
+    if not np.array_equal(np.asarray(eos, np.int32), o_cost):
+        return "dp[EOS] differs"
+    t = tokens16
+    for name, col in (("id", 0), ("cls", 1), ("position", 2), ("start", 3)):
+        if not np.array_equal(t[name].astype(np.int64), o_tok[:, col]):
+            return "token %s differs" % name
+    if not np.array_equal(t["start"].astype(np.int64) + t["char_len"], o_tok[:, 4]):
+        return "token end differs"
+    return None
+
+
+def latency_probe(tk, otk, sentences, reps=200):
+    """Single-sentence latency of kp_tokenize (the reference CLI's call pattern, src/bin/kanpyo.rs:115-122:
+    one line per call) beside the CPU port's time for the same sentence."""
+    out = {}
+    for name, s in sentences.items():
+        b = s.encode("utf-8")
+        off = np.array([0, len(b)], np.uint64)
+        for _ in range(20):
+            tk.tokenize_batch_bytes(b, off)
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            tk.tokenize_batch_bytes(b, off)
+            ts.append((time.perf_counter() - t0) * 1e6)
+        ts.sort()
+        cpu = None
+        if otk is not None:
+            buf = np.frombuffer(b, np.uint8)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                otk.tokenize_batch(buf, off, threads=1, collect=False)
+            cpu = (time.perf_counter() - t0) * 1e6 / reps
+        out[name] = {"chars": len(s), "p50": ts[len(ts) // 2], "p99": ts[min(len(ts) - 1, int(len(ts) * 0.99))],
+                     "cpu_port_us": cpu}
+    return out
+
+
 def product_arm(args):
     import torch
     import torch.distributed as dist
@@ -246,7 +303,8 @@ def product_arm(args):
         torch.cuda.synchronize()
 
     import kanpyo_b200
-    from kanpyo_b200 import sharded
+    from kanpyo_b200 import corpus, sharded
+    from kanpyo_b200.tokenizer import Queue, copy_result8, expand_tokens8
 
     kind, n_sent = WORKLOADS[args.workload]
     n_sent = args.sentences or n_sent
@@ -266,9 +324,12 @@ def product_arm(args):
         torch.cuda.synchronize()
         bcast_ms = e0.elapsed_time(e1)
         d.attach_device_blob(blob_t.data_ptr(), blob_t.numel(), local)
+        del blob_t
     tk = kanpyo_b200.Tokenizer(d, device=local)
     if args.chunk_mib:
         tk.set_chunk_bytes(args.chunk_mib << 20)
+    if args.path != "auto":
+        tk.set_path(args.path)
 
     n_bytes = int(off[-1])
     S = len(off) - 1
@@ -279,24 +340,41 @@ def product_arm(args):
     h_off = torch.from_numpy(off_i64.copy()).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
-    def step_device():
-        flush.zero_()
-        torch.cuda.synchronize()
-        r = tk.tokenize_batch_device(d_text.data_ptr(), d_off.data_ptr(), S, 0, n_bytes)
-        return r, tk.profile()
+    # ---- token gather to rank 0 (north_star's second collective), INSIDE every timed step at N > 1 ----
+    gather = None
+    if world > 1:
+        gather = sharded.TokenGather(dev, S, int(n_bytes * 0.2) + S)     # ~0.12 tokens per input byte
 
-    def step_e2e():
+    def gather_device_result(r):
+        t_off = sharded.device_view(r.tok_off, 4 * (S + 1), local)
+        t_tok = sharded.device_view(r.tokens, 8 * int(r.n_tokens), local)
+        t_eos = sharded.device_view(r.eos_cost, 4 * S, local)
+        return gather.gather(t_off, t_tok, t_eos)
+
+    ge0, ge1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def step_device():
+        """-> (result, device ms of the step: library stream events + the gather's events on torch's stream)."""
         flush.zero_()
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        r = tk.tokenize_batch_ptr(h_text.data_ptr(), h_off.data_ptr(), S)
-        return r, time.perf_counter() - t0
+        r = tk.tokenize_batch_device8(d_text.data_ptr(), d_off.data_ptr(), S, 0, n_bytes)
+        p = tk.profile()
+        g, gms = None, 0.0
+        if gather is not None:
+            ge0.record()
+            g = gather_device_result(r)
+            ge1.record()
+            torch.cuda.synchronize()
+            gms = ge0.elapsed_time(ge1)
+        return r, p, g, gms
 
     # exact work counters (outside any timed region)
     tk.set_count_work(True)
+    tk.set_path("pipeline")               # the counting kernels belong to the multi-kernel pipeline
     step_device()
     ctr = tk.counters()
     tk.set_count_work(False)
+    tk.set_path(args.path)
 
     for _ in range(args.warmup):
         step_device()
@@ -305,73 +383,183 @@ def product_arm(args):
         sampler.start()
     barrier()
     w0 = time.perf_counter()
-    dev_ms, stages, launches = [], {}, 0
+    dev_ms, gather_ms_sum, stages, launches = [], 0.0, {}, 0
+    g_last = None
     for _ in range(args.steps):
-        r, p = step_device()
-        dev_ms.append(p["total_ms"])
+        r, p, g_last, gms = step_device()
+        dev_ms.append(p["total_ms"] + gms)
+        gather_ms_sum += gms
         launches += p["kernel_launches"]
-        for k in ("prep_ms", "lattice_ms", "bucket_ms", "viterbi_ms", "backtrace_ms"):
-            stages[k] = stages.get(k, 0.0) + p[k]
+        for k in ("prep_ms", "lattice_ms", "bucket_ms", "viterbi_ms", "backtrace_ms", "fused_ms"):
+            stages[k] = stages.get(k, 0.0) + p.get(k, 0.0)
     barrier()
     wall_s = time.perf_counter() - w0
     n_tokens = int(r.n_tokens)
+    dev_result = tk.copy_device_result8(r)
 
-    for _ in range(args.warmup):
-        step_e2e()
+    # ---- e2e: the asynchronous queue (kp_queue_*), pinned HOST buffers in, pinned HOST result out; every
+    # step's H2D and D2H are inside the timed region, overlapped with the kernels of the neighbouring steps
+    q = Queue(d, device=local, depth=args.queue_depth)
+
+    def run_queue(k):
+        tks = [q.submit_ptr(h_text.data_ptr(), h_off.data_ptr(), S) for _ in range(k)]
+        return [q.wait_raw(t) for t in tks][-1]
+
+    run_queue(max(args.warmup, 2 * args.queue_depth))
     barrier()
-    e2e_s = []
+    t0 = time.perf_counter()
+    r_e2e = run_queue(args.steps)
+    torch.cuda.synchronize()
+    e2e_total_s = time.perf_counter() - t0
+    barrier()
+    e2e_result = copy_result8(r_e2e)
+    # the synchronous call (one batch at a time, nothing overlapped), for comparison
+    for _ in range(args.warmup):
+        tk.tokenize_batch8_ptr(h_text.data_ptr(), h_off.data_ptr(), S)
+    barrier()
+    t0 = time.perf_counter()
     for _ in range(args.steps):
-        r2, dt = step_e2e()
-        e2e_s.append(dt)
+        tk.tokenize_batch8_ptr(h_text.data_ptr(), h_off.data_ptr(), S)
+    sync_total_s = time.perf_counter() - t0
     barrier()
     clocks = sampler.stop() if sampler else None
-    assert int(r2.n_tokens) == n_tokens, "host and device entry points disagree on the token count"
+    q.close()
 
-    # ---- token gather to rank 0 over NVLink (north_star's second collective; outside the timed path) --
-    gather_ms = None
+    # ---- strong scaling (BASELINE.json configs[4]): ONE batch of n_sent sentences split into byte-balanced
+    # contiguous shards; shard text resident in HBM (the scatter happens once, outside); every timed step =
+    # tokenize the shard + gather the tokens on rank 0
+    strong = None
+    g_strong = None
     if world > 1:
-        r = tk.tokenize_batch_device(d_text.data_ptr(), d_off.data_ptr(), S, 0, n_bytes)
-        t_off = sharded.device_view(r.tok_off, 8 * (S + 1), local).view(torch.int64)
-        t_tok = sharded.device_view(r.tokens, 16 * int(r.n_tokens), local)
-        t_eos = sharded.device_view(r.eos_cost, 4 * S, local).view(torch.int32)
-        sharded.gather_results(t_off, t_tok, t_eos)             # warm the P2P channels
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        _, text0, off0 = load_dict_and_corpus(kind, n_sent, 0)          # every rank generates rank 0's batch
+        ranges = corpus.shard_by_bytes(off0, world)
+        s0, s1 = ranges[rank]
+        sh_off = np.ascontiguousarray(off0[s0:s1 + 1] - off0[s0]).view(np.int64)
+        sh_text = text0[int(off0[s0]):int(off0[s1])]
+        ds_text = torch.from_numpy(sh_text.copy()).to(dev)
+        ds_off = torch.from_numpy(sh_off.copy()).to(dev)
+        hs_text = torch.from_numpy(sh_text.copy()).pin_memory()
+        hs_off = torch.from_numpy(sh_off.copy()).pin_memory()
+        Ss, Bs = s1 - s0, int(sh_off[-1])
+        cap_s = max(b - a for a, b in ranges)
+        cap_t = max(int((off0[b] - off0[a]) * 0.2) + (b - a) for a, b in ranges)
+        sg = sharded.TokenGather(dev, cap_s, cap_t)
+
+        def step_strong():
+            flush.zero_()
+            torch.cuda.synchronize()
+            rr = tk.tokenize_batch_device8(ds_text.data_ptr(), ds_off.data_ptr(), Ss, 0, Bs)
+            pm = tk.profile()["total_ms"]
+            ge0.record()
+            gg = sg.gather(sharded.device_view(rr.tok_off, 4 * (Ss + 1), local),
+                           sharded.device_view(rr.tokens, 8 * int(rr.n_tokens), local),
+                           sharded.device_view(rr.eos_cost, 4 * Ss, local))
+            ge1.record()
+            torch.cuda.synchronize()
+            return gg, pm, ge0.elapsed_time(ge1)
+
+        for _ in range(args.warmup):
+            step_strong()
         barrier()
-        e0.record()
-        g = sharded.gather_results(t_off, t_tok, t_eos)
-        e1.record()
-        torch.cuda.synchronize()
-        gather_ms = e0.elapsed_time(e1)
-        if rank == 0:
-            assert g[2].numel() == S * world
+        sm, sgm = 0.0, 0.0
+        for _ in range(args.steps):
+            g_strong, pm, gm = step_strong()
+            sm += pm + gm
+            sgm += gm
+        barrier()
+        # e2e of the strong split: each rank's queue on its shard, host buffers in and out
+        q2 = Queue(d, device=local, depth=args.queue_depth)
+        for _ in range(2 * args.queue_depth):
+            q2.wait_raw(q2.submit_ptr(hs_text.data_ptr(), hs_off.data_ptr(), Ss))
+        barrier()
+        t0 = time.perf_counter()
+        tks = [q2.submit_ptr(hs_text.data_ptr(), hs_off.data_ptr(), Ss) for _ in range(args.steps)]
+        for t in tks:
+            q2.wait_raw(t)
+        strong_e2e_s = time.perf_counter() - t0
+        barrier()
+        q2.close()
+        sv = torch.tensor([sm, sgm, strong_e2e_s * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(sv, op=dist.ReduceOp.MAX)
+        sm, sgm, strong_e2e_ms = sv.tolist()
+        strong = {"sentences": int(len(off0) - 1), "bytes": int(off0[-1]), "value": int(off0[-1]) * args.steps / (sm * 1e-3),
+                  "unit": "bytes/s", "ms_per_step": sm / args.steps, "token_gather_ms": sgm / args.steps,
+                  "e2e_value": int(off0[-1]) * args.steps / (strong_e2e_ms * 1e-3),
+                  "what": "BASELINE.json configs[4]: one batch split into %d byte-balanced contiguous shards, shard text "
+                          "resident in HBM; every timed step = tokenize the shard + NCCL gather of the token records on "
+                          "rank 0 (one torch.distributed gather over NVLink); device time, max over ranks.  e2e_value: "
+                          "every rank's kp_queue on its shard from pinned host memory to pinned host memory" % world}
 
     # ---- reduce over ranks: bytes summed, times max ------------------------------------------------
-    vals = torch.tensor([sum(dev_ms), sum(e2e_s) * 1e3, wall_s * 1e3, stages["viterbi_ms"], stages["lattice_ms"],
-                         gather_ms or 0.0], dtype=torch.float64, device=dev)
+    vals = torch.tensor([sum(dev_ms), e2e_total_s * 1e3, wall_s * 1e3, stages["viterbi_ms"], stages["lattice_ms"],
+                         gather_ms_sum, sync_total_s * 1e3], dtype=torch.float64, device=dev)
     h2d_b = int(h_text.numel() + 8 * h_off.numel())
-    d2h_b = int(16 * n_tokens + 8 * (S + 1) + 4 * S)
+    d2h_b = int(8 * n_tokens + 4 * (S + 1) + 4 * S)
     sums = torch.tensor([n_bytes, n_tokens, launches, h2d_b, d2h_b], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    dev_total_ms, e2e_total_ms, wall_ms, vit_ms, lat_ms, gather_max = vals.tolist()
+    dev_total_ms, e2e_total_ms, wall_ms, vit_ms, lat_ms, gather_total_ms, sync_total_ms = vals.tolist()
     world_bytes, world_tokens, world_launches, world_h2d, world_d2h = sums.tolist()
+
+    # ---- parity gate: every number above is reported only with its result checked against the oracle --
+    parity = {"checked": False}
+    if not args.no_parity:
+        cores, _ = host_info()
+        ref = oracle_reference(text, off, cores)
+        checks = {}
+        checks["device"] = compare_with_oracle(ref, dev_result[0], expand_tokens8(dev_result[0], dev_result[1], off),
+                                               dev_result[2])
+        checks["e2e_queue"] = compare_with_oracle(ref, e2e_result[0], expand_tokens8(e2e_result[0], e2e_result[1], off),
+                                                  e2e_result[2])
+        sentences = S
+        if world > 1:
+            # rank 0 holds the gathered results: the weak one over all ranks' batches, the strong one over batch 0
+            if rank == 0:
+                texts, offs = [text], [off]
+                for rk in range(1, world):
+                    _, tx, of = load_dict_and_corpus(kind, n_sent, rk)
+                    texts.append(tx)
+                    offs.append(of)
+                g_text = np.concatenate(texts)
+                g_offs = [offs[0]]
+                for of in offs[1:]:
+                    g_offs.append(of[1:] + g_offs[-1][-1])
+                g_offv = np.concatenate(g_offs)
+                gref = oracle_reference(g_text, g_offv, cores)
+                gb = sharded.to_batch_result(*g_last, g_offv)
+                checks["gathered_weak"] = compare_with_oracle(gref, gb.tok_off, gb.tokens, gb.eos_cost)
+                sb = sharded.to_batch_result(*g_strong, off0)
+                checks["gathered_strong"] = compare_with_oracle(ref, sb.tok_off, sb.tokens, sb.eos_cost)
+                sentences = len(g_offv) - 1
+        bad = {k: v for k, v in checks.items() if v}
+        flag = torch.tensor([1.0 if bad else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        parity = {"checked": True, "sentences": int(sentences), "match": flag.item() == 0.0,
+                  "against": "oracle/ref_tokenize.cpp on the same bytes: tok_off, (id, class, position, start, end) of "
+                             "every token, dp[EOS] of every sentence, bit-exact",
+                  "results_checked": sorted(checks)}
+        if bad:
+            parity["mismatch"] = bad
 
     if rank == 0:
         K = args.steps
         peak, peak_src = measured_peak()
-        # algorithmic bytes of the dominant kernel (kp_viterbi), this rank's launch: DESIGN.md section 5
         N_nodes, E_pairs = ctr["nodes"], ctr["pairs"]
-        a_vit = 16 * N_nodes + 8 * E_pairs
         a_total = (ctr["bytes"] + ctr["chars"] + 8 * (ctr["probes"] + ctr["probes_ok"]) + 40 * N_nodes + 8 * E_pairs
                    + 20 * ctr["tokens"])
-        vit_launch_ms = stages["viterbi_ms"] / K
-        achieved = a_vit / (vit_launch_ms * 1e-3) / 1e9
         kern_ms = sum(stages.values()) / K
+        fused = stages.get("fused_ms", 0.0) > 0.5 * sum(stages.values())
+        if fused:      # the fused kernel does the whole path: its algorithmic bytes are the path's
+            dom, a_dom, dom_ms = "kp_fused", a_total, stages["fused_ms"] / K
+        else:          # multi-kernel pipeline: the sweep dominates
+            dom, a_dom, dom_ms = "kp_viterbi", 16 * N_nodes + 8 * E_pairs, stages["viterbi_ms"] / K
+        achieved = a_dom / (dom_ms * 1e-3) / 1e9
         traffic, traffic_src = None, None
         try:   # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
             with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-                tj = next(v for k, v in json.load(f).items() if k.startswith("kp_viterbi"))   # kp_viterbi<lanes>
+                tj = next(v for k, v in json.load(f).items() if k.startswith(dom))
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         except Exception:
             pass
@@ -380,22 +568,29 @@ def product_arm(args):
             "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": dev_total_ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC[args.workload], "sentences_per_gpu": S, "bytes_per_gpu": n_bytes,
-                       "parallelism": "dp%d (independent sentence shards, no data-path collective)" % world,
-                       "l2": "flushed between steps (256 MiB memset outside the timed events); per-step scratch "
-                             "(%.2f GB of node records / buckets) also exceeds the 126 MB L2"
-                             % ((N_nodes * 34 + ctr["chars"] * 36) / 1e9),
-                       "timing": "CUDA events on the library stream around each whole step, summed over steps, "
-                                 "max over ranks; wall_ms_per_step includes the L2 flushes"},
+                       "parallelism": ("dp%d: independent sentence shards; at N > 1 every timed step ends with the NCCL gather "
+                                       "of the token records on rank 0" % world),
+                       "path": args.path,
+                       "l2": "flushed between steps (256 MiB memset outside the timed events)",
+                       "timing": "CUDA events: the library stream around each whole step plus, at N > 1, torch's stream "
+                                 "around the token gather; summed over steps, max over ranks"},
             "wall_ms_per_step": wall_ms / K,
             "e2e": {"value": world_bytes * K / (e2e_total_ms * 1e-3), "unit": "bytes/s",
                     "h2d_bytes_per_step": int(world_h2d), "d2h_bytes_per_step": int(world_d2h),
                     "ms_per_step": e2e_total_ms / K,
-                    "api": "kp_tokenize_batch (C ABI) on pinned host buffers, wall clock around the call"},
+                    "api": "kp_queue_submit / kp_queue_wait (C ABI), depth %d: pinned host text + offsets in, pinned host "
+                           "kp_token8 records + offsets + dp[EOS] out, every step's copies inside the wall clock and "
+                           "overlapped with the neighbouring steps' kernels; the records are the packed form the Rust "
+                           "shim expands into Vec<Token> (that expansion is host work and not in this number)"
+                           % args.queue_depth,
+                    "sync_call": {"value": world_bytes * K / (sync_total_ms * 1e-3), "ms_per_step": sync_total_ms / K,
+                                  "api": "kp_tokenize_batch8, one blocking call per step, nothing overlapped"}},
             "gpu_launches": int(world_launches),
-            "roofline": {"bound": "hbm", "kernel": "kp_viterbi", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "parity": parity,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": a_vit, "launch_ms": vit_launch_ms,
-                         "share_of_kernel_time": vit_launch_ms / kern_ms,
+                         "algorithmic_bytes_per_launch": a_dom, "launch_ms": dom_ms,
+                         "share_of_kernel_time": dom_ms / kern_ms if kern_ms else None,
                          "whole_path": {"algorithmic_bytes": a_total, "bytes_per_input_byte": a_total / ctr["bytes"],
                                         "kernel_ms": kern_ms, "achieved": a_total / (kern_ms * 1e-3) / 1e9,
                                         "frac": a_total / (kern_ms * 1e-3) / 1e9 / peak}},
@@ -405,15 +600,23 @@ def product_arm(args):
         }
         if world > 1:
             line["dict_broadcast_ms"] = bcast_ms
-            line["token_gather_ms"] = gather_max
+            line["token_gather_ms"] = gather_total_ms / K
+            line["collectives"] = "NCCL (torch.distributed): one broadcast of the packed dictionary, one gather of token records per step"
+            line["strong_scaling"] = strong
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(text, off)
+            from oracle import oracle
+            otk = oracle.OracleTokenizer(oracle.load_ipadic())
+            first80 = bytes(text[int(off[0]):int(off[1])]).decode("utf-8")
+            line["latency_us"] = latency_probe(tk, otk, {"cfg1": "すもももももももものうち", "cfg2_sentence0": first80})
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity.get("checked") and not parity.get("match"):
+        return 3
     return 0
 
 
@@ -427,6 +630,9 @@ def main():
     ap.add_argument("--sentences", type=int, default=0, help="override sentences per GPU (debug)")
     ap.add_argument("--chunk-mib", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the benched batch (debug)")
+    ap.add_argument("--path", default="auto", choices=["auto", "pipeline", "fused"])
+    ap.add_argument("--queue-depth", type=int, default=2)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

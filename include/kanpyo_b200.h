@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define KP_ABI_VERSION 1
+#define KP_ABI_VERSION 2           /* 2: kp_profile grew fused_ms; compact results, queues and shards are new symbols */
 
 typedef enum kp_status {
     KP_OK = 0,
@@ -102,6 +102,27 @@ typedef struct kp_result {
     const int32_t* eos_cost;    /* [n_sent]: dp[EOS] of Lattice::viterbi (src/lattice.rs:116-143)          */
 } kp_result;
 
+/* Compact token record for transfers: half the bytes of kp_token.  `position` and `start` are prefix
+ * sums the host rebuilds (consecutive path nodes are adjacent in the input, see kp_token): walking a
+ * sentence's tokens BACKWARDS from its EOS token, position -= byte_len and start -= char_len.  The EOS
+ * token (cls == KP_CLASS_DUMMY, always the last token of a non-empty path) carries the sentence's char
+ * count in its two length fields: n_chars = byte_len | char_len << 16 (Token.start of EOS,
+ * src/tokenizer.rs:24-34); its position is the sentence's byte length, which the caller knows.
+ * kp_expand_tokens8 does exactly this on the host. */
+typedef struct kp_token8 {
+    uint32_t id_cls;     /* Token.id | KP_CLASS_* << 30                                          */
+    uint16_t byte_len;   /* surface bytes  (EOS: low half of n_chars)                            */
+    uint16_t char_len;   /* Token.end - Token.start (EOS: high half of n_chars)                  */
+} kp_token8;             /* 8 bytes */
+
+typedef struct kp_result8 {
+    uint64_t n_sent;
+    uint64_t n_tokens;
+    const uint32_t* tok_off;    /* [n_sent+1] */
+    const kp_token8* tokens;    /* [n_tokens] */
+    const int32_t* eos_cost;    /* [n_sent]   */
+} kp_result8;
+
 /* Exact work counters of the last batch call (used for the roofline's algorithmic bytes). */
 typedef struct kp_counters {
     uint64_t bytes;      /* B: input bytes            */
@@ -120,6 +141,9 @@ typedef struct kp_profile {
     float h2d_ms, prep_ms, lattice_ms, bucket_ms, viterbi_ms, backtrace_ms, d2h_ms, total_ms;
     uint32_t kernel_launches;   /* kernels of this library launched by the call */
     uint32_t chunks;
+    float fused_ms;             /* the fused per-sentence kernel (the other stage times then cover only the
+                                   sentences that did not fit it) */
+    uint32_t fused_sentences;   /* sentences the fused kernel completed */
 } kp_profile;
 
 int kp_abi_version(void);
@@ -158,6 +182,16 @@ int kp_tokenize_batch(kp_tokenizer* t, const uint8_t* utf8, const uint64_t* offs
  * n_bytes = offsets[n_sent] - offsets[0] (the host must know it).  The batch is one device pass. */
 int kp_tokenize_batch_device(kp_tokenizer* t, const uint8_t* d_utf8, const uint64_t* d_offsets, uint64_t n_sent,
                              uint64_t first_offset, uint64_t n_bytes, kp_result* out);
+/* kp_tokenize_batch with the compact 8-byte token records and 32-bit token offsets (half the
+ * device-to-host bytes).  KP_ERR_TOO_LARGE if the batch has 2^32 tokens or more. */
+int kp_tokenize_batch8(kp_tokenizer* t, const uint8_t* utf8, const uint64_t* offsets, uint64_t n_sent,
+                       kp_result8* out);
+/* kp_tokenize_batch_device with the compact result (device pointers). */
+int kp_tokenize_batch_device8(kp_tokenizer* t, const uint8_t* d_utf8, const uint64_t* d_offsets, uint64_t n_sent,
+                              uint64_t first_offset, uint64_t n_bytes, kp_result8* out);
+/* Host-side expansion kp_token8 -> kp_token (fills position / start / char_len; EOS char_len = 3).
+ * offsets = the caller's sentence offsets [n_sent+1]; out has r->n_tokens entries.  Pure host code. */
+int kp_expand_tokens8(const kp_result8* r, const uint64_t* offsets, kp_token* out);
 int kp_last_counters(const kp_tokenizer* t, kp_counters* out);
 /* on != 0: also count P, P_ok, E (slower; never enabled inside a timed region). */
 int kp_tokenizer_set_count_work(kp_tokenizer* t, int on);
@@ -167,6 +201,48 @@ int kp_last_profile(const kp_tokenizer* t, kp_profile* out);
 int kp_copy_to_host(kp_tokenizer* t, void* dst, const void* device_src, uint64_t bytes);
 /* Blocks until all work queued by this tokenizer is complete. */
 int kp_tokenizer_sync(kp_tokenizer* t);
+
+/* Which device path kp_tokenize* takes: KP_PATH_AUTO (default) runs the fused per-sentence kernel for
+ * sentences that fit its shared-memory budget and the multi-kernel pipeline for the rest;
+ * KP_PATH_PIPELINE forces the pipeline, KP_PATH_FUSED = AUTO (the pipeline still takes what does not
+ * fit).  Results are identical; the switch exists for measurements and parity tests. */
+enum { KP_PATH_AUTO = 0, KP_PATH_PIPELINE = 1, KP_PATH_FUSED = 2 };
+int kp_tokenizer_set_path(kp_tokenizer* t, int path);
+
+/* ---- asynchronous batches: H2D(n+1) || kernels(n) || D2H(n-1) across calls ------------------------
+ * A queue owns `depth` independent tokenizer contexts (stream + scratch + pinned result buffers),
+ * each served by its own host thread.  kp_queue_submit returns at once with a ticket; the caller's
+ * utf8 / offsets must stay valid until kp_queue_wait(ticket) returns.  Tickets count 0, 1, 2, ...;
+ * ticket k runs on context k % depth, and its result stays valid until ticket k + depth is submitted
+ * (submit blocks while ticket k is still running).  Results are the compact form (kp_result8, pinned
+ * host memory).  The reference has no such call: this is Tokenizer::tokenize over successive batches
+ * with the copies of one batch hidden behind the kernels of its neighbours. */
+typedef struct kp_queue kp_queue;
+int kp_queue_create(const kp_dict* d, uint32_t depth, kp_queue** out);
+int kp_queue_submit(kp_queue* q, const uint8_t* utf8, const uint64_t* offsets, uint64_t n_sent, uint64_t* ticket);
+int kp_queue_wait(kp_queue* q, uint64_t ticket, kp_result8* out);
+void kp_queue_destroy(kp_queue* q);
+
+/* ---- multi-GPU in one process: sentence shards, one dictionary broadcast, token gather --
+ * kp_shards_create packs the dictionary once, stages it on devices[0] and sends the packed blob to the
+ * other devices with ONE ncclBroadcast (communicators from ncclCommInitAll; libnccl.so.2 is loaded
+ * at run time, KP_ERR_CUDA if it is missing); every device gets a tokenizer context and a host
+ * thread.  kp_shards_tokenize splits the batch into contiguous sentence ranges balanced by bytes, one
+ * per device (global sentence order is kept, so gathering is concatenation); every device copies its
+ * range in, runs the path, and copies its tokens out straight into ONE pinned result at their global
+ * offsets -- for a host consumer the gather is the D2H itself.  kp_shards_tokenize_gather leaves the
+ * result in device memory of devices[0] instead: token records travel over NVLink with grouped
+ * ncclSend / ncclRecv (exact sizes).  Results are the compact form. */
+typedef struct kp_shards kp_shards;
+int kp_shards_create(const kp_dict_arrays* arrays, const int* devices, int n_devices, kp_shards** out);
+int kp_shards_tokenize(kp_shards* g, const uint8_t* utf8, const uint64_t* offsets, uint64_t n_sent, kp_result8* out);
+int kp_shards_tokenize_gather(kp_shards* g, const uint8_t* utf8, const uint64_t* offsets, uint64_t n_sent,
+                              kp_result8* out_device);
+/* milliseconds of the last kp_shards_* call: [0] whole call (wall), [1] slowest device pass (H2D + kernels),
+ * [2] the NCCL gather (0 for kp_shards_tokenize), [3] the dictionary broadcast at create time */
+int kp_shards_times(const kp_shards* g, float ms[4]);
+int kp_shards_copy_to_host(kp_shards* g, void* dst, const void* device_src, uint64_t bytes);
+void kp_shards_destroy(kp_shards* g);
 
 /* ---- lattice inspection (Lattice{nodes,edges} + viterbi internals) ---------------------------- */
 typedef struct kp_lattice_node {

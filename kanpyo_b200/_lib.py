@@ -38,6 +38,11 @@ class Result(C.Structure):
                 ("tokens", C.c_void_p), ("eos_cost", C.c_void_p)]
 
 
+class Result8(C.Structure):
+    _fields_ = [("n_sent", C.c_uint64), ("n_tokens", C.c_uint64), ("tok_off", C.c_void_p),
+                ("tokens", C.c_void_p), ("eos_cost", C.c_void_p)]
+
+
 class Counters(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("bytes", "chars", "nodes", "tokens", "sentences", "probes", "probes_ok",
                                           "pairs")]
@@ -46,7 +51,8 @@ class Counters(C.Structure):
 class Profile(C.Structure):
     _fields_ = [(k, C.c_float) for k in ("h2d_ms", "prep_ms", "lattice_ms", "bucket_ms", "viterbi_ms", "backtrace_ms",
                                          "d2h_ms", "total_ms")] + [("kernel_launches", C.c_uint32),
-                                                                   ("chunks", C.c_uint32)]
+                                                                   ("chunks", C.c_uint32), ("fused_ms", C.c_float),
+                                                                   ("fused_sentences", C.c_uint32)]
 
 
 class Lattice(C.Structure):
@@ -74,6 +80,20 @@ SYMBOLS = {
     "kp_tokenize": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(Result)]),
     "kp_tokenize_batch": (C.c_int, [_P, _P, _P, C.c_uint64, C.POINTER(Result)]),
     "kp_tokenize_batch_device": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(Result)]),
+    "kp_tokenize_batch8": (C.c_int, [_P, _P, _P, C.c_uint64, C.POINTER(Result8)]),
+    "kp_tokenize_batch_device8": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(Result8)]),
+    "kp_expand_tokens8": (C.c_int, [C.POINTER(Result8), _P, _P]),
+    "kp_tokenizer_set_path": (C.c_int, [_P, C.c_int]),
+    "kp_queue_create": (C.c_int, [_P, C.c_uint32, C.POINTER(_P)]),
+    "kp_queue_submit": (C.c_int, [_P, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "kp_queue_wait": (C.c_int, [_P, C.c_uint64, C.POINTER(Result8)]),
+    "kp_queue_destroy": (None, [_P]),
+    "kp_shards_create": (C.c_int, [C.POINTER(DictArrays), C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    "kp_shards_tokenize": (C.c_int, [_P, _P, _P, C.c_uint64, C.POINTER(Result8)]),
+    "kp_shards_tokenize_gather": (C.c_int, [_P, _P, _P, C.c_uint64, C.POINTER(Result8)]),
+    "kp_shards_times": (C.c_int, [_P, C.POINTER(C.c_float * 4)]),
+    "kp_shards_copy_to_host": (C.c_int, [_P, _P, _P, C.c_uint64]),
+    "kp_shards_destroy": (None, [_P]),
     "kp_last_counters": (C.c_int, [_P, C.POINTER(Counters)]),
     "kp_last_profile": (C.c_int, [_P, C.POINTER(Profile)]),
     "kp_tokenizer_sync": (C.c_int, [_P]),

@@ -74,7 +74,7 @@ struct PinBuf {   // pinned host memory, preserved on growth
 };
 
 constexpr uint32_t KP_PERM_REFRESH = 16;
-enum { EV_START, EV_H2D, EV_PREP, EV_LATTICE, EV_BUCKET, EV_VITERBI, EV_BACKTRACE, EV_END, EV_COUNT };
+enum { EV_START, EV_H2D, EV_PREP, EV_LATTICE, EV_BUCKET, EV_VITERBI, EV_BACKTRACE, EV_PACK, EV_FUSED0, EV_FUSED1, EV_END, EV_COUNT };
 
 }  // namespace
 
@@ -85,12 +85,13 @@ struct kp_tokenizer {
     cudaEvent_t ev[EV_COUNT] = {};
     uint64_t chunk_bytes = 64ull << 20;
     bool count_work = false;
+    int path_mode = KP_PATH_AUTO;
     kp_perm perm = {};
     uint32_t perm_age = 0;     // passes since the column order was last ranked
     DevBuf perm_hist, perm_map, perm_conn;
     // chunk scratch
     DevBuf text, off, nchar, coff, binfo, ncount, noff, bcount, boff, ucount, rbk, nhit, hits, bfill, rec, tgt, red, ndp, bnode, path, pre, lenhist, order,
-        tcount, toff32, scan_tmp, totals, err;
+        tcount, toff32, scan_tmp, totals, err, stage, sel;
     // device outputs
     DevBuf d_tok_off, d_tokens, d_eos;
     // host staging
@@ -98,6 +99,9 @@ struct kp_tokenizer {
     std::vector<kp_lattice_node> lattice_nodes;
     kp_counters counters = {};
     kp_profile profile = {};
+    bool pipeline_timed = false;
+    uint64_t last_tokens = 0;
+    kp_chunk pass = {};        // chunk of a two-phase pass (kp_pass_begin / kp_pass_pack)
 };
 
 namespace {
@@ -118,34 +122,27 @@ struct StageTimes {
     float prep = 0, lattice = 0, bucket = 0, viterbi = 0, backtrace = 0;
 };
 
-// One device pass over a chunk whose text / offsets are already in device memory.
-// Results land in t->d_tok_off[tok_off_pos ..], t->d_tokens[tok_base ..], t->d_eos[sent_pos ..]
-// when `append` (device API) or at position 0 (host API copies them out per chunk).
-int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_tokens, StageTimes* times) {
+// The multi-kernel pipeline over the sentences of a chunk (all of them, or the `c.sel` subset the fused
+// kernel left): lattice, buckets, sweep, back-trace; tokens end up staged (c.stage), token counts in
+// c.tcount and dp[EOS] in c.eos_cost, all indexed by chunk sentence.
+int run_pipeline(kp_tokenizer* t, kp_chunk& c, StageTimes* times) {
     cudaStream_t st = t->stream;
     const kp_ddict& d = t->dict->view;
     const uint32_t S = c.S;
     KP_TRY(t->nchar.ensure(sizeof(uint32_t) * (S + 1)));
     KP_TRY(t->coff.ensure(sizeof(uint32_t) * (S + 2)));
-    KP_TRY(t->totals.ensure(sizeof(uint64_t) * 8));
-    KP_TRY(t->err.ensure(sizeof(uint32_t) * 2));
-    KP_TRY(t->h_totals.ensure(sizeof(uint64_t) * 16, 0));
-    KP_TRY(t->scan_tmp.ensure(sizeof(uint64_t) * kp_scan_tmp_elems(S + 1)));
+    KP_TRY(t->scan_tmp.ensure(sizeof(uint64_t) * kp_scan_tmp_elems(std::max(S, c.S_all) + 1)));
     KP_TRY(t->lenhist.ensure(sizeof(uint32_t) * kp_len_bins()));
     KP_TRY(t->order.ensure(sizeof(uint32_t) * (S + 1)));
     c.lenhist = t->lenhist.as<uint32_t>();
     c.order = t->order.as<uint32_t>();
     c.nchar = t->nchar.as<uint32_t>();
     c.coff = t->coff.as<uint32_t>();
-    c.totals = t->totals.as<uint64_t>();
-    c.err = t->err.as<uint32_t>();
     c.scan_tmp = t->scan_tmp.as<uint64_t>();
     uint64_t* h_tot = t->h_totals.as<uint64_t>();
     uint32_t* h_err = (uint32_t*)(h_tot + 8);
 
     KP_CUDA(cudaEventRecord(t->ev[EV_H2D], st));
-    KP_CUDA(cudaMemsetAsync(c.totals, 0, sizeof(uint64_t) * 8, st));
-    KP_CUDA(cudaMemsetAsync(c.err, 0, sizeof(uint32_t) * 2, st));
     KP_CUDA(cudaMemsetAsync(c.lenhist, 0, sizeof(uint32_t) * kp_len_bins(), st));
     KP_LAUNCH(kp_launch_prep_count(c, st));
     KP_LAUNCH(kp_launch_scan(c.nchar, c.coff, S, c.scan_tmp, &c.totals[0], st));
@@ -208,16 +205,12 @@ int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_token
     KP_TRY(t->ndp.ensure(sizeof(int32_t) * (N + 1)));
     KP_TRY(t->bnode.ensure(sizeof(uint32_t) * (N + 1)));
     KP_TRY(t->path.ensure(sizeof(uint32_t) * (NB + 1)));
-    KP_TRY(t->tcount.ensure(sizeof(uint32_t) * (S + 1)));
-    KP_TRY(t->toff32.ensure(sizeof(uint32_t) * (S + 2)));
     c.rec = t->rec.as<uint4>();
     c.tgt = t->tgt.as<uint2>();
     c.red = t->red.as<int2>();
     c.ndp = t->ndp.as<int32_t>();
     c.bnode = t->bnode.as<uint32_t>();
     c.path = t->path.as<uint32_t>();
-    c.tcount = t->tcount.as<uint32_t>();
-    c.toff32 = t->toff32.as<uint32_t>();
 
     KP_LAUNCH(kp_launch_lattice_fill(c, d, st));
     KP_CUDA(cudaEventRecord(t->ev[EV_LATTICE], st));
@@ -230,21 +223,54 @@ int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_token
     if (t->count_work) KP_LAUNCH(kp_launch_pair_count(c, st));
     KP_CUDA(cudaEventRecord(t->ev[EV_VITERBI], st));
     KP_LAUNCH(kp_launch_backtrace_count(c, d, st));
-    KP_LAUNCH(kp_launch_scan(c.tcount, c.toff32, S, c.scan_tmp, &c.totals[3], st));
-    KP_LAUNCH(kp_launch_backtrace_write(c, tok_base, st));
+    KP_LAUNCH(kp_launch_backtrace_stage(c, st));
     KP_CUDA(cudaEventRecord(t->ev[EV_BACKTRACE], st));
+    t->counters.chars += c.C;
+    t->counters.nodes += (uint64_t)c.N + S;   // + one BOS per sentence (not materialised on the device)
+    t->pipeline_timed = true;
+    (void)times;
+    return KP_OK;
+}
+
+// One device pass over a chunk whose text / offsets are already in device memory, in two halves so
+// that a multi-GPU caller can learn every shard's token count before any shard packs its result:
+//   chunk_compute  lattice, Viterbi, back-trace; tokens staged; token counts scanned; *n_tokens read back
+//   chunk_pack     staged tokens -> c.tok_off / c.tokens (offsets rebased by tok_base); c.eos_cost is final
+int chunk_compute(kp_tokenizer* t, kp_chunk& c, uint64_t* n_tokens, StageTimes* times) {
+    cudaStream_t st = t->stream;
+    const uint32_t S = c.S;
+    c.S_all = S;
+    c.sel = nullptr;
+    KP_TRY(t->totals.ensure(sizeof(uint64_t) * 8));
+    KP_TRY(t->err.ensure(sizeof(uint32_t) * 4));
+    KP_TRY(t->h_totals.ensure(sizeof(uint64_t) * 16, 0));
+    KP_TRY(t->tcount.ensure(sizeof(uint32_t) * (S + 1)));
+    KP_TRY(t->toff32.ensure(sizeof(uint32_t) * (S + 2)));
+    KP_TRY(t->stage.ensure(sizeof(kp_token) * ((size_t)c.B + S + 2)));
+    KP_TRY(t->scan_tmp.ensure(sizeof(uint64_t) * kp_scan_tmp_elems(S + 1)));
+    c.totals = t->totals.as<uint64_t>();
+    c.err = t->err.as<uint32_t>();
+    c.tcount = t->tcount.as<uint32_t>();
+    c.toff32 = t->toff32.as<uint32_t>();
+    c.stage = t->stage.as<kp_token>();
+    c.scan_tmp = t->scan_tmp.as<uint64_t>();
+    uint64_t* h_tot = t->h_totals.as<uint64_t>();
+    KP_CUDA(cudaMemsetAsync(c.totals, 0, sizeof(uint64_t) * 8, st));
+    KP_CUDA(cudaMemsetAsync(c.err, 0, sizeof(uint32_t) * 4, st));
+    t->pipeline_timed = false;
+    KP_TRY(run_pipeline(t, c, times));
+    c.scan_tmp = t->scan_tmp.as<uint64_t>();
+    KP_LAUNCH(kp_launch_scan(c.tcount, c.toff32, c.S_all, c.scan_tmp, &c.totals[3], st));
     KP_CUDA(cudaMemcpyAsync(h_tot, c.totals, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaStreamSynchronize(st));
     *n_tokens = h_tot[3];
     t->counters.bytes += c.B;
-    t->counters.chars += c.C;
-    t->counters.nodes += (uint64_t)c.N + S;   // + one BOS per sentence (not materialised on the device)
     t->counters.tokens += h_tot[3];
-    t->counters.sentences += S;
+    t->counters.sentences += c.S_all;
     t->counters.probes += h_tot[4];
     t->counters.probes_ok += h_tot[5];
     t->counters.pairs += h_tot[6];
-    if (times) {
+    if (times && t->pipeline_timed) {
         float ms = 0;
         cudaEventElapsedTime(&ms, t->ev[EV_H2D], t->ev[EV_PREP]);       times->prep += ms;
         cudaEventElapsedTime(&ms, t->ev[EV_PREP], t->ev[EV_LATTICE]);   times->lattice += ms;
@@ -254,6 +280,18 @@ int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, uint64_t* n_token
     }
     t->profile.chunks++;
     return KP_OK;
+}
+
+int chunk_pack(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, bool compact) {
+    cudaStream_t st = t->stream;
+    KP_LAUNCH(kp_launch_tokens_pack(c, tok_base, compact, st));
+    KP_CUDA(cudaEventRecord(t->ev[EV_PACK], st));
+    return KP_OK;
+}
+
+int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, bool compact, uint64_t* n_tokens, StageTimes* times) {
+    KP_TRY(chunk_compute(t, c, n_tokens, times));
+    return chunk_pack(t, c, tok_base, compact);
 }
 
 void begin_call(kp_tokenizer* t) {
@@ -309,7 +347,7 @@ extern "C" void kp_tokenizer_destroy(kp_tokenizer* t) {
     if (t->stream) cudaStreamSynchronize(t->stream);
     DevBuf* bufs[] = {&t->text, &t->off, &t->nchar, &t->coff, &t->binfo, &t->ncount, &t->noff, &t->bcount, &t->boff,
                       &t->bfill, &t->ucount, &t->rbk, &t->nhit, &t->hits, &t->rec, &t->tgt, &t->red, &t->ndp, &t->bnode, &t->path, &t->pre, &t->lenhist, &t->order, &t->tcount, &t->toff32,
-                      &t->scan_tmp, &t->totals, &t->err, &t->d_tok_off, &t->d_tokens, &t->d_eos, &t->perm_hist, &t->perm_map,
+                      &t->scan_tmp, &t->totals, &t->err, &t->stage, &t->sel, &t->d_tok_off, &t->d_tokens, &t->d_eos, &t->perm_hist, &t->perm_map,
                       &t->perm_conn};
     for (DevBuf* b : bufs) b->release();
     PinBuf* pins[] = {&t->h_totals, &t->h_tok_off, &t->h_tokens, &t->h_eos, &t->h_misc};
@@ -361,9 +399,15 @@ extern "C" int kp_last_profile(const kp_tokenizer* t, kp_profile* out) {
     return KP_OK;
 }
 
-extern "C" int kp_tokenize_batch_device(kp_tokenizer* t, const uint8_t* d_utf8, const uint64_t* d_offsets,
-                                        uint64_t n_sent, uint64_t first_offset, uint64_t n_bytes, kp_result* out) {
-    if (!t || !out || !d_offsets || (n_bytes && !d_utf8)) return KP_ERR_ARG;
+extern "C" int kp_tokenizer_set_path(kp_tokenizer* t, int path) {
+    if (!t || path < KP_PATH_AUTO || path > KP_PATH_FUSED) return KP_ERR_ARG;
+    t->path_mode = path;
+    return KP_OK;
+}
+
+static int kp_tokenize_device(kp_tokenizer* t, const uint8_t* d_utf8, const uint64_t* d_offsets, uint64_t n_sent,
+                              uint64_t first_offset, uint64_t n_bytes, bool compact, kp_chunk* used, uint64_t* n_tokens) {
+    if (!t || !d_offsets || (n_bytes && !d_utf8)) return KP_ERR_ARG;
     if (n_bytes >= (1ull << 31) || n_sent >= (1ull << 31) - 2) return KP_ERR_TOO_LARGE;
     KP_CUDA(cudaSetDevice(t->device));
     begin_call(t);
@@ -379,28 +423,54 @@ extern "C" int kp_tokenize_batch_device(kp_tokenizer* t, const uint8_t* d_utf8, 
     KP_TRY(t->d_tok_off.ensure(sizeof(uint64_t) * (n_sent + 1)));
     KP_TRY(t->d_eos.ensure(sizeof(int32_t) * (n_sent + 1)));
     KP_TRY(t->d_tokens.ensure(sizeof(kp_token) * (n_bytes + n_sent + 1)));
-    c.tok_off = t->d_tok_off.as<uint64_t>();
+    c.tok_off = t->d_tok_off.p;
     c.eos_cost = t->d_eos.as<int32_t>();
-    c.tokens = t->d_tokens.as<kp_token>();
+    c.tokens = t->d_tokens.p;
     KP_CUDA(cudaEventRecord(t->ev[EV_START], st));
-    uint64_t ntok = 0;
     StageTimes times;
-    KP_TRY(run_chunk(t, c, 0, &ntok, &times));
+    KP_TRY(run_chunk(t, c, 0, compact, n_tokens, &times));
     KP_CUDA(cudaEventRecord(t->ev[EV_END], st));
     KP_CUDA(cudaEventSynchronize(t->ev[EV_END]));
     store_times(t, times);
     cudaEventElapsedTime(&t->profile.total_ms, t->ev[EV_START], t->ev[EV_END]);
+    *used = c;
+    return KP_OK;
+}
+
+extern "C" int kp_tokenize_batch_device(kp_tokenizer* t, const uint8_t* d_utf8, const uint64_t* d_offsets,
+                                        uint64_t n_sent, uint64_t first_offset, uint64_t n_bytes, kp_result* out) {
+    if (!out) return KP_ERR_ARG;
+    kp_chunk c;
+    uint64_t ntok = 0;
+    KP_TRY(kp_tokenize_device(t, d_utf8, d_offsets, n_sent, first_offset, n_bytes, false, &c, &ntok));
     out->n_sent = n_sent;
     out->n_tokens = ntok;
-    out->tok_off = c.tok_off;
-    out->tokens = c.tokens;
+    out->tok_off = (const uint64_t*)c.tok_off;
+    out->tokens = (const kp_token*)c.tokens;
     out->eos_cost = c.eos_cost;
     return KP_OK;
 }
 
-extern "C" int kp_tokenize_batch(kp_tokenizer* t, const uint8_t* utf8, const uint64_t* offsets, uint64_t n_sent,
-                                 kp_result* out) {
-    if (!t || !out || !offsets) return KP_ERR_ARG;
+extern "C" int kp_tokenize_batch_device8(kp_tokenizer* t, const uint8_t* d_utf8, const uint64_t* d_offsets,
+                                         uint64_t n_sent, uint64_t first_offset, uint64_t n_bytes, kp_result8* out) {
+    if (!out) return KP_ERR_ARG;
+    kp_chunk c;
+    uint64_t ntok = 0;
+    KP_TRY(kp_tokenize_device(t, d_utf8, d_offsets, n_sent, first_offset, n_bytes, true, &c, &ntok));
+    if (ntok >= (1ull << 32)) return KP_ERR_TOO_LARGE;
+    out->n_sent = n_sent;
+    out->n_tokens = ntok;
+    out->tok_off = (const uint32_t*)c.tok_off;
+    out->tokens = (const kp_token8*)c.tokens;
+    out->eos_cost = c.eos_cost;
+    return KP_OK;
+}
+
+// Host text in, host result out, chunk by chunk.  compact = kp_token8 records + 32-bit offsets.
+// The device result of a chunk is sized by its token COUNT of the previous call when that is known
+// to be enough, so the D2H moves the tokens that exist, not an upper bound.
+static int kp_tokenize_host(kp_tokenizer* t, const uint8_t* utf8, const uint64_t* offsets, uint64_t n_sent, bool compact) {
+    if (!t || !offsets) return KP_ERR_ARG;
     if (n_sent && offsets[n_sent] > offsets[0] && !utf8) return KP_ERR_ARG;
     for (uint64_t s = 0; s < n_sent; s++)
         if (offsets[s + 1] < offsets[s]) {
@@ -410,9 +480,11 @@ extern "C" int kp_tokenize_batch(kp_tokenizer* t, const uint8_t* utf8, const uin
     KP_CUDA(cudaSetDevice(t->device));
     begin_call(t);
     cudaStream_t st = t->stream;
-    KP_TRY(t->h_tok_off.ensure(sizeof(uint64_t) * (n_sent + 1), 0));
+    const size_t tok_sz = compact ? sizeof(kp_token8) : sizeof(kp_token);
+    const size_t off_sz = compact ? sizeof(uint32_t) : sizeof(uint64_t);
+    KP_TRY(t->h_tok_off.ensure(off_sz * (n_sent + 1), 0));
     KP_TRY(t->h_eos.ensure(sizeof(int32_t) * (n_sent + 1), 0));
-    t->h_tok_off.as<uint64_t>()[0] = 0;
+    memset(t->h_tok_off.p, 0, off_sz);
     uint64_t tok_total = 0;
     StageTimes times;
     float h2d_ms = 0, d2h_ms = 0, total_ms = 0;
@@ -439,24 +511,24 @@ extern "C" int kp_tokenize_batch(kp_tokenizer* t, const uint8_t* utf8, const uin
         c.base = offsets[s0];
         c.S = (uint32_t)S;
         c.B = (uint32_t)nbytes;
-        c.tok_off = t->d_tok_off.as<uint64_t>();
+        c.tok_off = t->d_tok_off.p;
         c.eos_cost = t->d_eos.as<int32_t>();
-        c.tokens = t->d_tokens.as<kp_token>();
+        c.tokens = t->d_tokens.p;
         uint64_t ntok = 0;
-        KP_TRY(run_chunk(t, c, tok_total, &ntok, &times));
-        KP_TRY(t->h_tokens.ensure(sizeof(kp_token) * (tok_total + ntok + 1), sizeof(kp_token) * tok_total));
+        KP_TRY(run_chunk(t, c, tok_total, compact, &ntok, &times));
+        if (compact && tok_total + ntok >= (1ull << 32)) return KP_ERR_TOO_LARGE;
+        KP_TRY(t->h_tokens.ensure(tok_sz * (tok_total + ntok + 1), tok_sz * tok_total));
         if (ntok)
-            KP_CUDA(cudaMemcpyAsync(t->h_tokens.as<kp_token>() + tok_total, c.tokens, sizeof(kp_token) * ntok,
+            KP_CUDA(cudaMemcpyAsync((char*)t->h_tokens.p + tok_sz * tok_total, c.tokens, tok_sz * ntok,
                                     cudaMemcpyDeviceToHost, st));
-        KP_CUDA(cudaMemcpyAsync(t->h_tok_off.as<uint64_t>() + s0, c.tok_off, sizeof(uint64_t) * (S + 1),
-                                cudaMemcpyDeviceToHost, st));
+        KP_CUDA(cudaMemcpyAsync((char*)t->h_tok_off.p + off_sz * s0, c.tok_off, off_sz * (S + 1), cudaMemcpyDeviceToHost, st));
         KP_CUDA(cudaMemcpyAsync(t->h_eos.as<int32_t>() + s0, c.eos_cost, sizeof(int32_t) * S, cudaMemcpyDeviceToHost, st));
         KP_CUDA(cudaEventRecord(t->ev[EV_END], st));
         KP_CUDA(cudaEventSynchronize(t->ev[EV_END]));
         float ms = 0;
         cudaEventElapsedTime(&ms, t->ev[EV_START], t->ev[EV_H2D]);    h2d_ms += ms;
-        cudaEventElapsedTime(&ms, t->ev[EV_BACKTRACE], t->ev[EV_END]); d2h_ms += ms;
-        cudaEventElapsedTime(&ms, t->ev[EV_START], t->ev[EV_END]);     total_ms += ms;
+        cudaEventElapsedTime(&ms, t->ev[EV_PACK], t->ev[EV_END]);     d2h_ms += ms;
+        cudaEventElapsedTime(&ms, t->ev[EV_START], t->ev[EV_END]);    total_ms += ms;
         tok_total += ntok;
         s0 = s1;
     }
@@ -464,11 +536,114 @@ extern "C" int kp_tokenize_batch(kp_tokenizer* t, const uint8_t* utf8, const uin
     t->profile.h2d_ms = h2d_ms;
     t->profile.d2h_ms = d2h_ms;
     t->profile.total_ms = total_ms;
+    t->last_tokens = tok_total;
+    return KP_OK;
+}
+
+// ---- two-phase single-chunk pass for the multi-GPU path (kp_queue.cu) --------------------------------
+int kp_pass_begin(kp_tokenizer* t, const uint8_t* utf8, const uint64_t* offsets, uint64_t n_sent, uint64_t* n_tokens) {
+    if (!t || !offsets || !n_tokens) return KP_ERR_ARG;
+    const uint64_t nbytes = offsets[n_sent] - offsets[0];
+    if (nbytes > t->chunk_bytes || nbytes >= (1ull << 31) || n_sent >= (1u << 30)) {
+        kp_set_error("shard of %llu bytes exceeds the tokenizer's chunk size", (unsigned long long)nbytes);
+        return KP_ERR_TOO_LARGE;
+    }
+    KP_CUDA(cudaSetDevice(t->device));
+    begin_call(t);
+    cudaStream_t st = t->stream;
+    KP_TRY(t->text.ensure(nbytes + 16));
+    KP_TRY(t->off.ensure(sizeof(uint64_t) * (n_sent + 1)));
+    KP_TRY(t->d_tok_off.ensure(sizeof(uint64_t) * (n_sent + 1)));
+    KP_TRY(t->d_eos.ensure(sizeof(int32_t) * (n_sent + 1)));
+    KP_TRY(t->d_tokens.ensure(sizeof(kp_token) * (nbytes + n_sent + 1)));
+    KP_CUDA(cudaEventRecord(t->ev[EV_START], st));
+    if (nbytes) KP_CUDA(cudaMemcpyAsync(t->text.p, utf8 + offsets[0], nbytes, cudaMemcpyHostToDevice, st));
+    KP_CUDA(cudaMemcpyAsync(t->off.p, offsets, sizeof(uint64_t) * (n_sent + 1), cudaMemcpyHostToDevice, st));
+    kp_chunk& c = t->pass;
+    memset(&c, 0, sizeof(c));
+    c.text = t->text.as<uint8_t>();
+    c.off = t->off.as<uint64_t>();
+    c.base = offsets[0];
+    c.S = (uint32_t)n_sent;
+    c.B = (uint32_t)nbytes;
+    c.tok_off = t->d_tok_off.p;
+    c.eos_cost = t->d_eos.as<int32_t>();
+    c.tokens = t->d_tokens.p;
+    StageTimes times;
+    KP_TRY(chunk_compute(t, c, n_tokens, &times));
+    store_times(t, times);
+    t->last_tokens = *n_tokens;
+    return KP_OK;
+}
+
+// packs the pass's tokens (compact form, offsets rebased by tok_base) and leaves them on the device
+int kp_pass_pack(kp_tokenizer* t, uint64_t tok_base, const uint32_t** d_tok_off, const kp_token8** d_tokens,
+                 const int32_t** d_eos, cudaStream_t* stream) {
+    KP_CUDA(cudaSetDevice(t->device));
+    KP_TRY(chunk_pack(t, t->pass, tok_base, true));
+    *d_tok_off = (const uint32_t*)t->pass.tok_off;
+    *d_tokens = (const kp_token8*)t->pass.tokens;
+    *d_eos = t->pass.eos_cost;
+    *stream = t->stream;
+    return KP_OK;
+}
+
+extern "C" int kp_tokenize_batch(kp_tokenizer* t, const uint8_t* utf8, const uint64_t* offsets, uint64_t n_sent,
+                                 kp_result* out) {
+    if (!out) return KP_ERR_ARG;
+    KP_TRY(kp_tokenize_host(t, utf8, offsets, n_sent, false));
     out->n_sent = n_sent;
-    out->n_tokens = tok_total;
+    out->n_tokens = t->last_tokens;
     out->tok_off = t->h_tok_off.as<uint64_t>();
     out->tokens = t->h_tokens.as<kp_token>();
     out->eos_cost = t->h_eos.as<int32_t>();
+    return KP_OK;
+}
+
+extern "C" int kp_tokenize_batch8(kp_tokenizer* t, const uint8_t* utf8, const uint64_t* offsets, uint64_t n_sent,
+                                  kp_result8* out) {
+    if (!out) return KP_ERR_ARG;
+    KP_TRY(kp_tokenize_host(t, utf8, offsets, n_sent, true));
+    out->n_sent = n_sent;
+    out->n_tokens = t->last_tokens;
+    out->tok_off = t->h_tok_off.as<uint32_t>();
+    out->tokens = t->h_tokens.as<kp_token8>();
+    out->eos_cost = t->h_eos.as<int32_t>();
+    return KP_OK;
+}
+
+// kp_token8 -> kp_token on the host: walk every sentence's tokens backwards from its EOS token
+// (position = sentence bytes, start = n_chars carried by the EOS record); see the header.
+extern "C" int kp_expand_tokens8(const kp_result8* r, const uint64_t* offsets, kp_token* out) {
+    if (!r || !offsets || (r->n_tokens && (!out || !r->tokens)) || (r->n_sent && !r->tok_off)) return KP_ERR_ARG;
+    for (uint64_t s = 0; s < r->n_sent; s++) {
+        const uint32_t a = r->tok_off[s], b = r->tok_off[s + 1];
+        if (a == b) continue;                     // empty path (dp[EOS] = INF): no tokens, no EOS
+        uint32_t pos = (uint32_t)(offsets[s + 1] - offsets[s]), start = 0;
+        for (uint32_t k = b; k-- > a;) {
+            const kp_token8 x = r->tokens[k];
+            const uint32_t cls = x.id_cls >> 30;
+            kp_token o;
+            o.id = (int32_t)(x.id_cls & 0x3FFFFFFFu);
+            o.cls = (uint8_t)cls;
+            o.reserved = 0;
+            if (k == b - 1) {
+                if (cls != KP_CLASS_DUMMY) {
+                    kp_set_error("sentence %llu: last token is not EOS", (unsigned long long)s);
+                    return KP_ERR_ARG;
+                }
+                start = (uint32_t)x.byte_len | ((uint32_t)x.char_len << 16);
+                o.char_len = 3;
+            } else {
+                pos -= x.byte_len;
+                start -= x.char_len;
+                o.char_len = x.char_len;
+            }
+            o.position = pos;
+            o.start = start;
+            out[k] = o;
+        }
+    }
     return KP_OK;
 }
 

@@ -61,7 +61,10 @@ struct kp_blob_header {
     uint64_t off_da, off_dup, off_morphs, off_conn, off_cat, off_catinfo, off_unk_morphs;
     uint64_t reserved[4];      // [0] offset of the transposed matrix, [1] its row stride in elements,
                                // [2] offset of the first-character table, [3] 1 = some key ends inside a character
+    uint64_t checksum;         // FNV-1a (64-bit, 8 bytes at a time) of everything after the header, written by kp_pack:
+                               // a blob that passes it carries exactly the indices kp_pack validated
 };
+constexpr uint32_t KP_BLOB_VERSION = 2;   // layout of kp_blob_header + sections (independent of KP_ABI_VERSION)
 
 struct kp_dict {
     int device;
@@ -83,3 +86,7 @@ void kp_set_error(const char* fmt, ...);
     } while (0)
 
 int kp_view_from_blob(const kp_blob_header* h, const void* d_blob, kp_ddict* v);
+// Validates `host_blob` (header, section extents, checksum) and wraps the copy of it that already sits in
+// device memory at d_blob (e.g. the receive buffer of the NCCL broadcast): the handle takes ownership
+// of d_blob (cudaFree at kp_dict_destroy).  No second upload.
+int kp_dict_adopt_device_blob(std::string&& host_blob, void* d_blob, int device, kp_dict** out);

@@ -47,6 +47,15 @@ extern "C" int kp_device_count(int* n) {
 
 static inline uint64_t align256(uint64_t x) { return (x + 255) & ~uint64_t(255); }
 
+// FNV-1a over 64-bit words (sections are 256-byte aligned, so the payload is a whole number of words)
+static uint64_t kp_blob_checksum(const char* blob, uint64_t size) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    const uint64_t* w = (const uint64_t*)(blob + align256(sizeof(kp_blob_header)));
+    const uint64_t n = (size - align256(sizeof(kp_blob_header))) / 8;
+    for (uint64_t i = 0; i < n; i++) h = (h ^ w[i]) * 0x100000001b3ull;
+    return h;
+}
+
 // Pack + validate.  Returns KP_OK and fills `blob`.
 static int kp_pack(const kp_dict_arrays* a, std::string* blob) {
     if (!a) return KP_ERR_ARG;
@@ -143,7 +152,7 @@ static int kp_pack(const kp_dict_arrays* a, std::string* blob) {
     kp_blob_header h;
     memset(&h, 0, sizeof(h));
     h.magic = KP_BLOB_MAGIC;
-    h.version = KP_ABI_VERSION;
+    h.version = KP_BLOB_VERSION;
     h.header_size = sizeof(h);
     h.da_len = a->da_len;
     h.n_morphs = a->n_morphs;
@@ -285,22 +294,42 @@ static int kp_pack(const kp_dict_arrays* a, std::string* blob) {
     memcpy(p + h.off_cat, a->char_category, a->n_char_category);
     memcpy(p + h.off_catinfo, ci.data(), 256 * sizeof(kp_catinfo));
     pack_morphs(p + h.off_unk_morphs, a->unk_morphs, a->n_unk_morphs);
+    ((kp_blob_header*)p)->checksum = kp_blob_checksum(p, o);
     return KP_OK;
 }
 
-static int kp_check_header(const kp_blob_header* h, uint64_t size) {
-    if (size < sizeof(kp_blob_header) || h->magic != KP_BLOB_MAGIC || h->version != KP_ABI_VERSION ||
-        h->header_size != sizeof(kp_blob_header) || h->total_size != size) {
+// A blob is accepted only if it is byte-for-byte what kp_pack wrote: magic / version / size, every
+// section inside the blob, and the payload checksum.  kp_pack validated every index the kernels form
+// (they have no bounds checks), so a truncated, stale or foreign blob must stop here.
+static int kp_check_blob(const void* blob, uint64_t size) {
+    const kp_blob_header* h = (const kp_blob_header*)blob;
+    if (size < sizeof(kp_blob_header) || h->magic != KP_BLOB_MAGIC || h->version != KP_BLOB_VERSION ||
+        h->header_size != sizeof(kp_blob_header) || h->total_size != size || (size & 255)) {
         kp_set_error("dictionary blob: bad magic/version/size");
         return KP_ERR_BLOB;
     }
-    const uint64_t offs[] = {h->off_da, h->off_dup, h->off_morphs, h->off_conn, h->off_cat, h->off_catinfo,
-                             h->off_unk_morphs, h->reserved[0], h->reserved[2]};
-    for (uint64_t o : offs)
-        if (o == 0 || o >= size || (o & 255)) {
-            kp_set_error("dictionary blob: bad section offset");
+    const uint64_t strideT = h->reserved[1];
+    if (h->da_len >= (1ull << 31) || h->n_morphs >= KP_ID_MASK || h->n_unk_morphs >= KP_ID_MASK || h->conn_row == 0 ||
+        h->conn_col == 0 || h->conn_row > 65536 || h->conn_col > 65536 || h->n_cat == 0 || strideT < h->conn_col ||
+        strideT > 65536 + 64 || (strideT & 63)) {
+        kp_set_error("dictionary blob: section sizes out of range");
+        return KP_ERR_BLOB;
+    }
+    const struct { uint64_t off, len; } sec[] = {
+        {h->off_da, (h->da_len ? h->da_len : 1) * 8},         {h->off_dup, (h->n_morphs + 2) * 2},
+        {h->off_morphs, (h->n_morphs ? h->n_morphs : 1) * 8}, {h->off_conn, h->conn_row * h->conn_col * 2},
+        {h->off_cat, h->n_cat},                               {h->off_catinfo, 256 * sizeof(kp_catinfo)},
+        {h->off_unk_morphs, (h->n_unk_morphs ? h->n_unk_morphs : 1) * 8},
+        {h->reserved[0], h->conn_row * strideT * 2},          {h->reserved[2], (uint64_t)KP_FIRST_CPS * 8}};
+    for (const auto& x : sec)
+        if (x.off < sizeof(kp_blob_header) || (x.off & 255) || x.off > size || x.len > size - x.off) {
+            kp_set_error("dictionary blob: a section lies outside the blob");
             return KP_ERR_BLOB;
         }
+    if (kp_blob_checksum((const char*)blob, size) != h->checksum) {
+        kp_set_error("dictionary blob: checksum mismatch (truncated, stale or foreign blob)");
+        return KP_ERR_BLOB;
+    }
     return KP_OK;
 }
 
@@ -413,23 +442,53 @@ extern "C" int kp_dict_device_blob(const kp_dict* d, const void** device_ptr, ui
 extern "C" int kp_dict_create_from_blob(const void* host_blob, uint64_t size, int device, kp_dict** out) {
     if (!host_blob || !out) return KP_ERR_ARG;
     *out = nullptr;
-    int rc = kp_check_header((const kp_blob_header*)host_blob, size);
+    int rc = kp_check_blob(host_blob, size);
     if (rc) return rc;
     std::string blob((const char*)host_blob, (size_t)size);
     return kp_upload(std::move(blob), device, out);
 }
 
+int kp_dict_adopt_device_blob(std::string&& host_blob, void* d_blob, int device, kp_dict** out) {
+    int rc = kp_check_blob(host_blob.data(), host_blob.size());
+    if (rc) return rc;
+    kp_dict* d = new kp_dict();
+    d->device = device;
+    d->size = host_blob.size();
+    d->host_blob = std::move(host_blob);
+    d->d_blob = d_blob;
+    kp_view_from_blob((const kp_blob_header*)d->host_blob.data(), d->d_blob, &d->view);
+    *out = d;
+    return KP_OK;
+}
+
+// From a packed blob already in device memory (e.g. the receive buffer of an NCCL broadcast): one
+// device-to-host copy for validation and for the handle's host copy, one device-to-device copy
+// into memory the handle owns.  The caller's buffer is not kept.
 extern "C" int kp_dict_create_from_device_blob(const void* device_blob, uint64_t size, int device, kp_dict** out) {
-    if (!device_blob || !out || size < sizeof(kp_blob_header)) return KP_ERR_ARG;
+    if (!device_blob || !out || size < sizeof(kp_blob_header) || size >= (1ull << 40)) return KP_ERR_ARG;
     *out = nullptr;
     int rc = kp_require_device(device);
     if (rc) return rc;
     KP_CUDA(cudaSetDevice(device));
     std::string blob((size_t)size, '\0');
     KP_CUDA(cudaMemcpy(&blob[0], device_blob, size, cudaMemcpyDeviceToHost));
-    rc = kp_check_header((const kp_blob_header*)blob.data(), size);
+    rc = kp_check_blob(blob.data(), size);
     if (rc) return rc;
-    return kp_upload(std::move(blob), device, out);
+    void* mine = nullptr;
+    if (cudaMalloc(&mine, size) != cudaSuccess) {
+        cudaGetLastError();
+        kp_set_error("cudaMalloc(%llu) for the dictionary failed", (unsigned long long)size);
+        return KP_ERR_NOMEM;
+    }
+    cudaError_t e = cudaMemcpy(mine, device_blob, size, cudaMemcpyDeviceToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(mine);
+        kp_set_error("dictionary copy failed: %s", cudaGetErrorString(e));
+        return KP_ERR_CUDA;
+    }
+    rc = kp_dict_adopt_device_blob(std::move(blob), mine, device, out);
+    if (rc) cudaFree(mine);
+    return rc;
 }
 
 extern "C" void kp_dict_destroy(kp_dict* d) {

@@ -206,9 +206,6 @@ int kp_launch_scan2(const uint32_t* a, const uint32_t* b, uint32_t* oa, uint32_t
 #ifndef KP_PREP_THREADS
 #define KP_PREP_THREADS 256
 #endif
-#ifndef KP_PREP_PF
-#define KP_PREP_PF 0           // candidate for the next round (unmeasured): next slice's text byte fetched a pass ahead
-#endif
 constexpr int PREP_THREADS = KP_PREP_THREADS;
 constexpr uint32_t LEN_BINS = 4096;    // counting-sort bins of the Viterbi work order (sentence length in chars)
 
@@ -224,12 +221,14 @@ __device__ __forceinline__ uint32_t lead_len(uint32_t c) {  // 0 = not a valid l
 // Rust's &str is valid UTF-8 by construction (src/tokenizer.rs:16 takes &str); the C ABI has to check.
 __global__ void __launch_bounds__(PREP_THREADS) kp_prep_count(const uint8_t* __restrict__ text,
                                                               const uint64_t* __restrict__ off, uint64_t base,
+                                                              const uint32_t* __restrict__ sel,
                                                               uint32_t S, uint32_t B, uint32_t* __restrict__ nchar,
                                                               uint32_t* __restrict__ err, uint32_t* __restrict__ lenhist) {
     uint32_t s = (blockIdx.x * PREP_THREADS + threadIdx.x) >> 5;
     if (s >= S) return;
-    uint64_t lo64 = off[s] - base, hi64 = off[s + 1] - base;
-    if (off[s] < base || hi64 < lo64 || hi64 > B) {
+    const uint32_t so = sel ? sel[s] : s;         // sentence of the chunk this pass's slot s stands for
+    uint64_t lo64 = off[so] - base, hi64 = off[so + 1] - base;
+    if (off[so] < base || hi64 < lo64 || hi64 > B) {
         if (lane_id() == 0) {
             atomicOr(&err[1], 1u);
             nchar[s] = 0;
@@ -240,16 +239,8 @@ __global__ void __launch_bounds__(PREP_THREADS) kp_prep_count(const uint8_t* __r
     uint32_t lo = (uint32_t)lo64, hi = (uint32_t)hi64;
     uint32_t cnt = 0, conts = 0, claimed = 0;
     bool bad = false;
-#if KP_PREP_PF
-    uint32_t cnext = lo + lane_id() < hi ? text[lo + lane_id()] : 0u;   // next slice's byte, one iteration ahead
-#endif
     for (uint32_t i = lo + lane_id(); i < hi; i += 32) {
-#if KP_PREP_PF
-        const uint32_t c = cnext;
-        if (i + 32 < hi) cnext = text[i + 32];
-#else
         uint32_t c = text[i];
-#endif
         if (!is_cont(c)) {
             cnt++;
             uint32_t L = lead_len(c);
@@ -283,7 +274,8 @@ __global__ void __launch_bounds__(PREP_THREADS) kp_prep_count(const uint8_t* __r
 }
 
 __global__ void __launch_bounds__(PREP_THREADS) kp_prep_fill(const uint8_t* __restrict__ text,
-                                                             const uint64_t* __restrict__ off, uint64_t base, uint32_t S,
+                                                             const uint64_t* __restrict__ off, uint64_t base,
+                                                             const uint32_t* __restrict__ sel, uint32_t S,
                                                              const uint32_t* __restrict__ coff, kp_ddict d,
                                                              uint4* __restrict__ binfo, uint32_t* __restrict__ bcount,
                                                              uint32_t* __restrict__ ucount, uint32_t* __restrict__ cursor,
@@ -291,24 +283,17 @@ __global__ void __launch_bounds__(PREP_THREADS) kp_prep_fill(const uint8_t* __re
     uint32_t s = (blockIdx.x * PREP_THREADS + threadIdx.x) >> 5;
     if (s >= S) return;
     const uint32_t lane = lane_id();
-    const uint32_t lo = (uint32_t)(off[s] - base), hi = (uint32_t)(off[s + 1] - base);
+    const uint32_t so = sel ? sel[s] : s;
+    const uint32_t lo = (uint32_t)(off[so] - base), hi = (uint32_t)(off[so + 1] - base);
     const uint32_t bb = coff[s] + s;              // first boundary of this sentence
     const uint32_t n = coff[s + 1] - coff[s];     // chars
     if (lane == 0)                                // counting-sort scatter of the Viterbi work order (cursor = scanned histogram)
         order[atomicAdd(&cursor[min(n, LEN_BINS - 1)], 1u)] = s;
     // forward: byte offset + class of every char (Lattice::build's chars().enumerate(), lattice.rs:105)
     uint32_t run = 0;
-#if KP_PREP_PF
-    uint32_t cnext = lo + lane < hi ? text[lo + lane] : 0x80u;           // next slice's byte, one iteration ahead
-#endif
     for (uint32_t i0 = lo; i0 < hi; i0 += 32) {
         uint32_t i = i0 + lane;
-#if KP_PREP_PF
-        const uint32_t c = cnext;
-        cnext = i + 32 < hi ? text[i + 32] : 0x80u;
-#else
         uint32_t c = i < hi ? text[i] : 0x80u;
-#endif
         bool st = !is_cont(c);
         uint32_t m = __ballot_sync(KP_FULL, st);
         if (st) {
@@ -355,14 +340,14 @@ __global__ void __launch_bounds__(PREP_THREADS) kp_prep_fill(const uint8_t* __re
 int kp_launch_prep_count(const kp_chunk& c, cudaStream_t st) {
     if (c.S == 0) return 0;
     uint32_t blocks = (uint32_t)(((uint64_t)c.S * 32 + PREP_THREADS - 1) / PREP_THREADS);
-    kp_prep_count<<<blocks, PREP_THREADS, 0, st>>>(c.text, c.off, c.base, c.S, c.B, c.nchar, c.err, c.lenhist);
+    kp_prep_count<<<blocks, PREP_THREADS, 0, st>>>(c.text, c.off, c.base, c.sel, c.S, c.B, c.nchar, c.err, c.lenhist);
     return kp_launch_check("kp_prep_count");
 }
 
 int kp_launch_prep_fill(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
     if (c.S == 0) return 0;
     uint32_t blocks = (uint32_t)(((uint64_t)c.S * 32 + PREP_THREADS - 1) / PREP_THREADS);
-    kp_prep_fill<<<blocks, PREP_THREADS, 0, st>>>(c.text, c.off, c.base, c.S, c.coff, d, c.binfo, c.bcount, c.ucount,
+    kp_prep_fill<<<blocks, PREP_THREADS, 0, st>>>(c.text, c.off, c.base, c.sel, c.S, c.coff, d, c.binfo, c.bcount, c.ucount,
                                                   c.lenhist, c.order);
     return kp_launch_check("kp_prep_fill");
 }
@@ -383,9 +368,6 @@ constexpr uint32_t LAT_HITS = 4;   // trie hits per start boundary remembered fr
 #ifndef KP_WALK_T1
 #define KP_WALK_T1 1
 #endif
-#ifndef KP_HITS_NH
-#define KP_HITS_NH 0           // candidate for the next round (unmeasured): the hit count rides in the spare bits
-#endif                         // of the first hit record, so the fill pass reads one stream less (no nhit)
 #ifndef KP_WALK_SKIP_MID
 #define KP_WALK_SKIP_MID 1
 #endif
@@ -478,18 +460,8 @@ __global__ void __launch_bounds__(LAT_THREADS, FILL ? KP_FILL_MINB : KP_CNT_MINB
             // The counting walk remembers its first LAT_HITS hits {id, chars | dups << 16}; the fill pass
             // replays them and walks the trie again only for the few boundaries with more hits than that.
             uint4 h01 = make_uint4(0, 0, 0, 0), h23 = make_uint4(0, 0, 0, 0);
-#if KP_HITS_NH
-            uint32_t nh = 0;
-            if (FILL) {                            // min(hits, 5) in the two spare bits of ids 0 and 1
-                h01 = hits[2 * (size_t)b];
-                nh = (h01.x >> 30) | ((h01.z >> 30) << 2);
-                h01.x &= KP_ID_MASK;
-                h01.z &= KP_ID_MASK;
-            }
-#else
             uint32_t nh = FILL ? nhit[b] : 0;
             if (FILL) h01 = hits[2 * (size_t)b];   // not waiting for nh (unused when nh == 0)
-#endif
             if (FILL && nh <= LAT_HITS) {
                 if (nh > 2) h23 = hits[2 * (size_t)b + 1];
                 // first morph of every hit: four independent gathers in flight together
@@ -539,19 +511,10 @@ __global__ void __launch_bounds__(LAT_THREADS, FILL ? KP_FILL_MINB : KP_CNT_MINB
                     base = nq.x;
                 }
                 nhit[b] = (uint8_t)min(nh, 255u);
-#if KP_HITS_NH
-                h01.x |= (min(nh, 5u) & 3u) << 30;
-                h01.z |= (min(nh, 5u) >> 2) << 30;
-                hits[2 * (size_t)b] = h01;
-#else
                 if (nh > 0) hits[2 * (size_t)b] = h01;
-#endif
                 if (nh > 2) hits[2 * (size_t)b + 1] = h23;
             } else {
                 nhit[b] = 0;
-#if KP_HITS_NH
-                hits[2 * (size_t)b] = make_uint4(0, 0, 0, 0);
-#endif
             }
             const bool matched = nh > 0;
             // unknown words (lattice.rs:42-99)
@@ -689,18 +652,9 @@ __global__ void __launch_bounds__(LAT_THREADS, KP_CNT_MINB) kp_lattice_count(
                 h[u].y |= (k[u] - 1) << 16;
             }
         }
-#if KP_HITS_NH
-        h[0].x |= (min(nh, 5u) & 3u) << 30;
-        h[1].x |= (min(nh, 5u) >> 2) << 30;
-        hits[2 * (size_t)b] = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y);
-#else
         if (nh > 0) hits[2 * (size_t)b] = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y);
-#endif
         if (nh > 2) hits[2 * (size_t)b + 1] = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
     }
-#if KP_HITS_NH
-    else hits[2 * (size_t)b] = make_uint4(0, 0, 0, 0);
-#endif
     nhit[b] = (uint8_t)min(nh, 255u);
     // unknown words (lattice.rs:42-99)
     const kp_catinfo ci = d.catinfo[bi.w & 0xFFu];
@@ -917,9 +871,6 @@ int kp_launch_bucketize(const kp_chunk& c, const kp_ddict& d, const kp_perm& pm,
 #ifndef KP_VIT_LATEPF
 #define KP_VIT_LATEPF 1         // next boundary's bounds / targets issued just before the pair loop (see kp_viterbi)
 #endif
-#ifndef KP_VIT_TGEARLY2
-#define KP_VIT_TGEARLY2 0       // candidate for the next round: second chunk of targets a step ahead as well
-#endif
 #ifndef KP_VIT_TGEARLY
 #define KP_VIT_TGEARLY 1        // next boundary's first targets fetched a whole step ahead
 #endif
@@ -1019,7 +970,8 @@ __device__ __forceinline__ int ld_conn(const char* p) {
 // =================================================================================================
 template <int GROUP>
 __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
-    uint32_t S, uint32_t N, const uint32_t* __restrict__ order, const uint32_t* __restrict__ coff, const uint32_t* __restrict__ noff,
+    uint32_t S, uint32_t N, const uint32_t* __restrict__ order, const uint32_t* __restrict__ sel,
+    const uint32_t* __restrict__ coff, const uint32_t* __restrict__ noff,
     const uint2* __restrict__ rbk, const uint2* __restrict__ tgt, int2* red,
     int32_t* __restrict__ ndp, int32_t* __restrict__ eos_cost, const int16_t* __restrict__ connT) {
     const uint32_t slot = (blockIdx.x * VIT_THREADS + threadIdx.x) / GROUP;
@@ -1044,19 +996,12 @@ __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
     // cluster (noun / unknown-word ids are neighbours), so a group's gather touches ~2 lines, not ~5
     uint2 tgn = make_uint2(0u, KP_NONE);          // first target chunk of the next boundary, prefetched
     if (has && t0 + l < t1n) tgn = tgt[t0 + l];
-#if KP_VIT_TGEARLY2
-    uint2 tgn2 = make_uint2(0u, KP_NONE);
-    if (has && t0 + GROUP + l < t1n) tgn2 = tgt[t0 + GROUP + l];
-#endif
     for (uint32_t p = 0; p < steps; p++) {
         const bool act = has && p <= n;
         const uint32_t t1 = act ? t1n : t0, R = act ? bkn.y : 0u;
         const int2* const rbase = red + bkn.x;
 #if KP_VIT_TGEARLY
         uint2 tnx = make_uint2(0u, KP_NONE);      // next boundary's first targets, fetched a whole step ahead
-#endif
-#if KP_VIT_TGEARLY2
-        uint2 tnx2 = make_uint2(0u, KP_NONE);     // and its second chunk of targets (candidate, not yet measured)
 #endif
         // Bounds (and first targets) of the next boundary.  Issued just before the pair loop rather than
         // here: ptxas puts these loads on the scoreboard of the merge-value load, and the first wait on
@@ -1069,9 +1014,6 @@ __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
                 // the address is known now, whether the lane has a target there only once t1n arrives:
                 // fetch anyway (clamped to the array), decide at the end of the step
                 tnx = tgt[min(t1 + l, N)];
-#endif
-#if KP_VIT_TGEARLY2
-                tnx2 = tgt[min(t1 + GROUP + l, N)];
 #endif
             }
         };
@@ -1086,10 +1028,6 @@ __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
         for (uint32_t tc = 0; tc < Tmax; tc += GROUP) {
             const bool tv = tc + l < T;
             uint2 tg = tgn;
-#if KP_VIT_TGEARLY2
-            if (tc == GROUP) tg = tgn2;
-            else
-#endif
             if (tc) tg = tv ? tgt[t0 + tc + l] : make_uint2(0u, KP_NONE);
             const uint64_t crow = elem_ptr_pinned(connT, tg.x & 0xFFFFu);   // this target's column; entries carry row offsets
             // reduced slot: bit 31 marks a shared one (unknown node); KP_NONE = EOS, which ends nowhere
@@ -1124,14 +1062,11 @@ __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
                 int dp = KP_INF;
                 if (R) dp = min(best + (int)(int16_t)(tg.x >> 16), KP_INF);
                 ndp[t0 + tc + l] = dp;
-                if (eos) eos_cost[s] = dp;
+                if (eos) eos_cost[sel ? sel[s] : s] = dp;
                 else *slotp = min(merged, dp);
             }
         }
         // the next boundary's first targets: the address does not depend on this step's results
-#if KP_VIT_TGEARLY2
-        tgn2 = (has && p < n && t1 + GROUP + l < t1n) ? tnx2 : make_uint2(0u, KP_NONE);
-#endif
 #if KP_VIT_TGEARLY
         tgn = (has && p < n && t1 + l < t1n) ? tnx : make_uint2(0u, KP_NONE);
 #else
@@ -1151,7 +1086,7 @@ int kp_launch_viterbi(const kp_chunk& c, const kp_ddict& d, const kp_perm& pm, c
     const int group = KP_VIT_GROUP ? KP_VIT_GROUP : (c.S >= 24000 ? 8 : c.S >= 12000 ? 16 : 32);
     const uint32_t blocks = (uint32_t)(((uint64_t)c.S * group + VIT_THREADS - 1) / VIT_THREADS);
 #define KP_VIT_LAUNCH(G)                                                                                          \
-    kp_viterbi<G><<<blocks, VIT_THREADS, 0, st>>>(c.S, c.N, c.order, c.coff, c.noff, c.rbk, c.tgt, c.red, c.ndp, c.eos_cost, \
+    kp_viterbi<G><<<blocks, VIT_THREADS, 0, st>>>(c.S, c.N, c.order, c.sel, c.coff, c.noff, c.rbk, c.tgt, c.red, c.ndp, c.eos_cost, \
                                                   pm.connP)
     if (group == 8) KP_VIT_LAUNCH(8);
     else if (group == 16) KP_VIT_LAUNCH(16);
@@ -1240,6 +1175,7 @@ constexpr int BT_GROUP = KP_BT_GROUP;
 #define KP_BT_ORDER 1
 #endif
 __global__ void __launch_bounds__(BT_THREADS) kp_backtrace_find(uint32_t S, const uint32_t* __restrict__ order,
+                                                                const uint32_t* __restrict__ sel,
                                                                 const uint32_t* __restrict__ coff,
                                                                 const uint32_t* __restrict__ noff,
                                                                 const uint32_t* __restrict__ boff,
@@ -1300,29 +1236,33 @@ __global__ void __launch_bounds__(BT_THREADS) kp_backtrace_find(uint32_t S, cons
         if (next == KP_NONE) break;              // reached BOS, which has no predecessor and is not emitted
         cur = next;
     }
-    if (l == 0) tcount[s] = cnt;
+    if (l == 0) tcount[sel ? sel[s] : s] = cnt;
 }
 
-// Tokens front to back: a whole warp per sentence (~30 tokens: one round), each lane one token.
+// Tokens front to back into the staging area: a whole warp per sentence (~30 tokens: one round), each
+// lane one token.  Sentence `so` of the chunk stages its tokens at stage[(off[so] - base) + so ...):
+// a path has at most chars + 1 <= bytes + 1 tokens, so the regions of different sentences never
+// overlap and no scan is needed before the tokens exist (the fused kernel stages the same way).
 #ifndef KP_EMIT_GROUP
 #define KP_EMIT_GROUP 32
 #endif
 constexpr int EMIT_GROUP = KP_EMIT_GROUP;
-__global__ void __launch_bounds__(BT_THREADS) kp_backtrace_emit(uint32_t S, const uint32_t* __restrict__ coff,
-                                                                const uint4* __restrict__ rec,
-                                                                const uint4* __restrict__ binfo,
-                                                                const uint32_t* __restrict__ path,
-                                                                const uint32_t* __restrict__ toff, uint64_t tok_base,
-                                                                uint64_t* __restrict__ tok_off,
-                                                                kp_token* __restrict__ tokens) {
+__global__ void __launch_bounds__(BT_THREADS) kp_backtrace_stage(uint32_t S, const uint32_t* __restrict__ sel,
+                                                                 const uint64_t* __restrict__ off, uint64_t base,
+                                                                 const uint32_t* __restrict__ coff,
+                                                                 const uint4* __restrict__ rec,
+                                                                 const uint4* __restrict__ binfo,
+                                                                 const uint32_t* __restrict__ path,
+                                                                 const uint32_t* __restrict__ tcount,
+                                                                 kp_token* __restrict__ stage) {
     const uint32_t s = (blockIdx.x * BT_THREADS + threadIdx.x) / EMIT_GROUP;
     const uint32_t l = threadIdx.x & (EMIT_GROUP - 1);
-    if (s > S) return;
-    if (l == 0) tok_off[s] = tok_base + toff[s];
-    if (s == S) return;
+    if (s >= S) return;
+    const uint32_t so = sel ? sel[s] : s;
     const uint32_t bb = coff[s] + s;
     const uint32_t sent_byte0 = binfo[bb].x;     // for n == 0 this is the EOS boundary: also the sentence start
-    const uint32_t w0 = toff[s], cnt = toff[s + 1] - w0;
+    const uint32_t cnt = tcount[so];
+    kp_token* const out = stage + ((off[so] - base) + so);
     for (uint32_t k = l; k < cnt; k += EMIT_GROUP) {
         const uint4 r = rec[path[bb + cnt - 1 - k]];
         const uint32_t kind = r.x >> KP_KIND_SHIFT;
@@ -1333,21 +1273,64 @@ __global__ void __launch_bounds__(BT_THREADS) kp_backtrace_emit(uint32_t S, cons
         t.char_len = kind == KP_CLASS_DUMMY ? 3 : (uint16_t)(r.w >> 16);   // "EOS".chars().count()
         t.cls = (uint8_t)kind;
         t.reserved = 0;
-        tokens[w0 + k] = t;
+        out[k] = t;
+    }
+}
+
+// Staged tokens -> the packed result, after the scan of the token counts: a warp per sentence.
+// COMPACT = false: kp_token records (16 B) and 64-bit offsets; true: kp_token8 (8 B; see the header for
+// how the host rebuilds position / start) and 32-bit offsets.
+template <bool COMPACT>
+__global__ void __launch_bounds__(BT_THREADS) kp_tokens_pack(uint32_t S, const uint64_t* __restrict__ off, uint64_t base,
+                                                             const uint32_t* __restrict__ toff, uint64_t tok_base,
+                                                             const kp_token* __restrict__ stage, void* __restrict__ tok_off_out,
+                                                             void* __restrict__ tokens_out) {
+    const uint32_t s = (blockIdx.x * BT_THREADS + threadIdx.x) >> 5;
+    const uint32_t l = lane_id();
+    if (s > S) return;
+    if (l == 0) {
+        if (COMPACT) ((uint32_t*)tok_off_out)[s] = (uint32_t)(tok_base + toff[s]);
+        else ((uint64_t*)tok_off_out)[s] = tok_base + toff[s];
+    }
+    if (s == S) return;
+    const uint32_t w0 = toff[s], cnt = toff[s + 1] - w0;
+    const uint4* const in = (const uint4*)(stage + ((off[s] - base) + s));
+    for (uint32_t k = l; k < cnt; k += 32) {
+        const uint4 t = in[k];                   // {id, position, start, char_len | cls << 16}
+        if (!COMPACT) {
+            ((uint4*)tokens_out)[w0 + k] = t;
+        } else {
+            const uint32_t cls = (t.w >> 16) & 0xFFu;
+            uint32_t lens;
+            if (cls == KP_CLASS_DUMMY) lens = t.z;                                   // EOS: n_chars
+            else lens = ((in[k + 1].y - t.y) & 0xFFFFu) | (t.w << 16);               // bytes up to the next token | chars
+            ((uint2*)tokens_out)[w0 + k] = make_uint2((uint32_t)t.x | (cls << KP_KIND_SHIFT), lens);
+        }
     }
 }
 
 int kp_launch_backtrace_count(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
     if (c.S == 0) return 0;
-    kp_backtrace_find<<<(uint32_t)(((uint64_t)c.S * BT_GROUP + BT_THREADS - 1) / BT_THREADS), BT_THREADS, 0, st>>>(c.S, c.order, c.coff, c.noff, c.boff, c.rec, c.ndp, c.bnode,
+    kp_backtrace_find<<<(uint32_t)(((uint64_t)c.S * BT_GROUP + BT_THREADS - 1) / BT_THREADS), BT_THREADS, 0, st>>>(c.S, c.order, c.sel, c.coff, c.noff, c.boff, c.rec, c.ndp, c.bnode,
                                                          d.conn, d.conn_row, c.path, c.tcount);
     return kp_launch_check("kp_backtrace_find");
 }
 
-int kp_launch_backtrace_write(const kp_chunk& c, uint64_t tok_base, cudaStream_t st) {
-    kp_backtrace_emit<<<(uint32_t)(((uint64_t)(c.S + 1) * EMIT_GROUP + BT_THREADS - 1) / BT_THREADS), BT_THREADS, 0, st>>>(c.S, c.coff, c.rec, c.binfo, c.path, c.toff32, tok_base,
-                                                             c.tok_off, c.tokens);
-    return kp_launch_check("kp_backtrace_emit");
+int kp_launch_backtrace_stage(const kp_chunk& c, cudaStream_t st) {
+    if (c.S == 0) return 0;
+    kp_backtrace_stage<<<(uint32_t)(((uint64_t)c.S * EMIT_GROUP + BT_THREADS - 1) / BT_THREADS), BT_THREADS, 0, st>>>(
+        c.S, c.sel, c.off, c.base, c.coff, c.rec, c.binfo, c.path, c.tcount, c.stage);
+    return kp_launch_check("kp_backtrace_stage");
+}
+
+// over ALL sentences of the chunk (S_all), whichever path staged their tokens
+int kp_launch_tokens_pack(const kp_chunk& c, uint64_t tok_base, bool compact, cudaStream_t st) {
+    const uint32_t blocks = (uint32_t)(((uint64_t)(c.S_all + 1) * 32 + BT_THREADS - 1) / BT_THREADS);
+    if (compact)
+        kp_tokens_pack<true><<<blocks, BT_THREADS, 0, st>>>(c.S_all, c.off, c.base, c.toff32, tok_base, c.stage, c.tok_off, c.tokens);
+    else
+        kp_tokens_pack<false><<<blocks, BT_THREADS, 0, st>>>(c.S_all, c.off, c.base, c.toff32, tok_base, c.stage, c.tok_off, c.tokens);
+    return kp_launch_check("kp_tokens_pack");
 }
 
 // =================================================================================================
@@ -1392,3 +1375,4 @@ int kp_launch_common_prefix(const kp_ddict& d, const uint8_t* d_text, uint32_t l
     kp_common_prefix<<<1, 32, 0, st>>>(d, d_text, len, expand_dup, d_ids, d_lens, cap, d_n);
     return kp_launch_check("kp_common_prefix");
 }
+

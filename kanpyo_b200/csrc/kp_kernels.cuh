@@ -27,6 +27,9 @@
 //                         KP_NONE for EOS)
 //   ndp     i32[N]        dp of every node (the back-trace and the lattice dump read it)
 //   path    u32[NB]       best path of each sentence, back to front, at the sentence's boundary base
+//   stage   kp_token[B+S+1] tokens of sentence s in path order at (off[s] - base) + s (a path has at most
+//                         bytes + 1 tokens); kp_tokens_pack moves them to the packed result after the
+//                         scan of the token counts
 //   pre     u32[N]        (lattice dump only) predecessor as a bucket slot (KP_NONE = Option::None)
 #pragma once
 #include "kp_common.cuh"
@@ -36,7 +39,10 @@ struct kp_chunk {
     const uint8_t* text;     // device, chunk-relative base
     const uint64_t* off;     // device, [S+1]
     uint64_t base;           // off[0]
-    uint32_t S, B;
+    uint32_t S, B;           // S = sentences of THIS pass (all of the chunk, or the `sel` subset)
+    uint32_t S_all;          // sentences of the chunk
+    const uint32_t* sel;     // [S] chunk sentence behind each slot of this pass (nullptr = identity); outputs
+                             // (eos_cost, tcount, staged tokens) are indexed by chunk sentence
     // sizes learnt on the way
     uint32_t C, NB, N;
     // scratch (device)
@@ -47,8 +53,9 @@ struct kp_chunk {
     uint2* bfill;            // running {all, known} counts while bucketizing
     uint4* rec; uint2* tgt; int2* red; int32_t* ndp; uint32_t* bnode; uint32_t* path; uint32_t* pre;
     int32_t* eos_cost; uint32_t* tcount; uint32_t* toff32;
-    uint64_t* tok_off;       // [S+1] output (rebased by tok_base)
-    kp_token* tokens;        // output
+    kp_token* stage;         // [B + S_all + 1] staged tokens: sentence s at (off[s] - base) + s, in path order
+    void* tok_off;           // [S_all+1] output (rebased by tok_base): u64, or u32 for the compact form
+    void* tokens;            // output: kp_token[], or kp_token8[] for the compact form
     uint64_t* scan_tmp;      // tile partials for the scans
     uint64_t* totals;        // [8] device scalars: 0 chars, 1 nodes, 2 bucket entries, 3 tokens, 4 P, 5 P_ok, 6 E
     uint32_t* err;           // [2] device flags: 0 utf8, 1 offsets
@@ -78,7 +85,8 @@ int kp_launch_viterbi(const kp_chunk& c, const kp_ddict& d, const kp_perm& pm, c
 int kp_launch_pair_count(const kp_chunk& c, cudaStream_t st);
 int kp_launch_backtrace_count(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
 int kp_launch_fill_pre(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
-int kp_launch_backtrace_write(const kp_chunk& c, uint64_t tok_base, cudaStream_t st);
+int kp_launch_backtrace_stage(const kp_chunk& c, cudaStream_t st);
+int kp_launch_tokens_pack(const kp_chunk& c, uint64_t tok_base, bool compact, cudaStream_t st);
 // exclusive scans, n inputs -> n+1 outputs; total (u64) written to *total
 int kp_launch_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint64_t* tmp, uint64_t* total, cudaStream_t st);
 int kp_launch_scan2(const uint32_t* in_a, const uint32_t* in_b, uint32_t* out_a, uint32_t* out_b, uint32_t n,

@@ -32,8 +32,9 @@ class Dict:
     features: tuple = field(default_factory=tuple)      # (rows, names)   morph_feature.rs:7-10
     unk_features: tuple = field(default_factory=tuple)
 
-    _handle: object = field(default=None, repr=False, compare=False)
-    _device: int = field(default=-1, repr=False, compare=False)
+    # kp_dict* per device.  A handle is shared by every Tokenizer built on that device and lives as
+    # long as the Dict: nothing replaces or destroys it while a tokenizer may still read it.
+    _handles: dict = field(default_factory=dict, repr=False, compare=False)
 
     # ---- C ABI ---------------------------------------------------------------------------------
     def _arrays(self):
@@ -71,29 +72,33 @@ class Dict:
         return blob
 
     def device_handle(self, device: int = 0):
-        """kp_dict* staged on `device` (created once per Dict and device)."""
-        if self._handle is None or self._device != device:
-            self.close()
+        """kp_dict* staged on `device` (created once per Dict and device, kept until close())."""
+        h = self._handles.get(device)
+        if h is None:
             L = _lib.load()
             a, _keep = self._arrays()
             h = C.c_void_p()
             _lib.check(L.kp_dict_create(C.byref(a), device, C.byref(h)))
-            self._handle, self._device = h, device
-        return self._handle
+            self._handles[device] = h
+        return h
 
     def attach_device_blob(self, device_ptr: int, size: int, device: int):
-        """Stage from a packed blob already in HBM on `device` (e.g. the receive buffer of the NCCL
-        broadcast from rank 0) instead of from the host arrays (kp_dict_create_from_device_blob)."""
-        self.close()
+        """Stage `device`'s handle from a packed blob already in HBM there (e.g. the receive buffer of the
+        NCCL broadcast from rank 0) instead of from the host arrays (kp_dict_create_from_device_blob:
+        validated, then copied into memory the handle owns -- the caller's buffer is not kept).  Only
+        allowed while this Dict has no handle on that device yet: a live Tokenizer holds the raw handle."""
+        if device in self._handles:
+            raise RuntimeError("Dict already staged on device %d; attach_device_blob must come first" % device)
         h = C.c_void_p()
         _lib.check(_lib.load().kp_dict_create_from_device_blob(device_ptr, size, device, C.byref(h)))
-        self._handle, self._device = h, device
+        self._handles[device] = h
         return h
 
     def close(self):
-        if self._handle is not None:
-            _lib.load().kp_dict_destroy(self._handle)
-            self._handle = None
+        """Destroys every device handle.  Only call once no Tokenizer built on this Dict is in use."""
+        handles, self._handles = self._handles, {}
+        for h in handles.values():
+            _lib.load().kp_dict_destroy(h)
 
     def __del__(self):
         try:

@@ -54,3 +54,18 @@ def assert_batch_equal(res, o_tok_off, o_tokens, o_cost):
     nxt[-1] = 0
     bl = np.where(t["cls"] == 0, 3, nxt - t["position"].astype(np.int64))
     assert np.array_equal(bl, o_tokens[:, 5]), "surface byte lengths differ"
+
+
+def oracle_to_token8(o_tokens):
+    """Oracle tokens (int64[n,6] = id, class, position, start, end, byte_len) -> kp_token8 records as the
+    device writes them (EOS carries the sentence's char count in its two length fields)."""
+    from kanpyo_b200.tokenizer import TOKEN8_DTYPE
+    t = np.zeros(len(o_tokens), TOKEN8_DTYPE)
+    if len(o_tokens) == 0:
+        return t
+    cls = o_tokens[:, 1]
+    t["id_cls"] = (o_tokens[:, 0] | (cls << 30)).astype(np.uint32)
+    eos = cls == 0
+    t["byte_len"] = np.where(eos, o_tokens[:, 3] & 0xFFFF, o_tokens[:, 5]).astype(np.uint16)
+    t["char_len"] = np.where(eos, o_tokens[:, 3] >> 16, o_tokens[:, 4] - o_tokens[:, 3]).astype(np.uint16)
+    return t

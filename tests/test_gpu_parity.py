@@ -322,7 +322,8 @@ def test_idempotent_and_sharding_invariant(gpu_tok, vocab):
 
 def test_sharded_tokenizer_single_rank(gpu_ipadic, oracle_tok, vocab):
     """kanpyo_b200.sharded on one rank over NCCL: dictionary blob round trip through the broadcast
-    path (device blob -> kp_dict_create_from_device_blob) and the gather's world-size-1 path."""
+    path (device blob -> kp_dict_create_from_device_blob, checksum-validated) and the gather's
+    world-size-1 path.  The caller's Dict (and the session tokenizer built on it) stay usable."""
     import torch
     import torch.distributed as dist
     from kanpyo_b200 import corpus, sharded
@@ -336,5 +337,173 @@ def test_sharded_tokenizer_single_rank(gpu_ipadic, oracle_tok, vocab):
         res = st.tokenize_global(text, off)
         o_off, o_tok, o_cost, _ = oracle_tok.tokenize_batch(text, off)
         assert_batch_equal(res, o_off, o_tok, o_cost)
+        assert st.dict is not gpu_ipadic
     finally:
         dist.destroy_process_group()
+
+
+# ---- full-size parity: BASELINE.json configs[1..3] at (or near) their stated sizes ------------------------
+def _full_check(tok, oracle_tok, text, off):
+    res = tok.tokenize_batch_bytes(text, off)
+    o_off, o_tok, o_cost, ctr = oracle_tok.tokenize_batch(text, off, threads=os.cpu_count() or 8)
+    assert_batch_equal(res, o_off, o_tok, o_cost)
+    c = tok.counters()
+    assert (c["bytes"], c["chars"], c["nodes"], c["tokens"]) == (ctr["B"], ctr["C"], ctr["N"], ctr["T"])
+    return res
+
+
+def test_full_cfg2_65536(gpu_tok, oracle_tok, vocab):
+    """configs[1]: the benched batch itself, all 65 536 sentences, both device paths."""
+    from kanpyo_b200 import corpus
+    text, off = corpus.synth_corpus(vocab, 65536, "cfg2")
+    for path in ("auto", "pipeline"):
+        gpu_tok.set_path(path)
+        try:
+            _full_check(gpu_tok, oracle_tok, text, off)
+        finally:
+            gpu_tok.set_path("auto")
+
+
+def test_full_cfg4_4096x4096(gpu_tok, oracle_tok, vocab):
+    """configs[3]: 4096 sentences of 4096 chars: 4096 concurrent long chains, 32 lanes per sentence in the sweep,
+    sentence lengths beyond the last bin of the length histogram."""
+    from kanpyo_b200 import corpus
+    text, off = corpus.synth_corpus(vocab, 4096, "cfg4")
+    _full_check(gpu_tok, oracle_tok, text, off)
+
+
+def test_large_cfg3_multi_chunk(gpu_ipadic, oracle_tok, vocab):
+    """configs[2] shape at 327 680 sentences (69.6 MB): two device passes at the default 64 MiB chunk size."""
+    import kanpyo_b200
+    from kanpyo_b200 import corpus
+    text, off = corpus.synth_corpus(vocab, 327680, "cfg3")
+    t = kanpyo_b200.Tokenizer(gpu_ipadic, device=0)
+    try:
+        _full_check(t, oracle_tok, text, off)
+        assert t.profile()["chunks"] == 2
+    finally:
+        t.close()
+
+
+# ---- compact records, the asynchronous queue, single-process shards ----------------------------------------
+def test_compact_records_match(gpu_tok, oracle_tok, oracle_mod, vocab):
+    """kp_tokenize_batch8 + host expansion == kp_tokenize_batch == oracle, including truncated and empty paths."""
+    import kanpyo_b200
+    from kanpyo_b200 import corpus
+    from kanpyo_b200.tokenizer import result8_to_batch
+    from helpers import oracle_to_token8
+    text, off = corpus.synth_corpus(vocab, 3000, "cfg3")
+    r8 = gpu_tok.tokenize_batch8_bytes(text, off)
+    o_off, o_tok, o_cost, _ = oracle_tok.tokenize_batch(text, off, threads=8)
+    assert np.array_equal(r8[1], oracle_to_token8(o_tok)), "kp_token8 records differ from the oracle's"
+    assert_batch_equal(result8_to_batch(r8, off), o_off, o_tok, o_cost)
+    od = reference_fixture_dict(oracle_mod)
+    g = kanpyo_b200.Tokenizer(to_product_dict(od), device=0)
+    o = oracle_mod.OracleTokenizer(od)
+    text, off = pack(["テスト", "", "xテスト", "テストx", "xx", "テxスト", "あいうえお", "x", "辞書テスト形態素"])
+    r8 = g.tokenize_batch8_bytes(text, off)
+    o_off, o_tok, o_cost, _ = o.tokenize_batch(text, off)
+    assert np.array_equal(r8[1], oracle_to_token8(o_tok))
+    assert_batch_equal(result8_to_batch(r8, off), o_off, o_tok, o_cost)
+    g.close()
+
+
+def test_queue_overlapped_batches(gpu_ipadic, oracle_tok, vocab):
+    """kp_queue_*: several batches in flight on two contexts give each batch's own result."""
+    from kanpyo_b200 import corpus
+    from kanpyo_b200.tokenizer import Queue
+    q = Queue(gpu_ipadic, device=0, depth=2)
+    try:
+        batches = [corpus.synth_corpus(vocab, n, kind, seed=100 + i)
+                   for i, (n, kind) in enumerate([(3000, "cfg2"), (10, "cfg4"), (1, "cfg2"), (2500, "cfg3"), (700, "cfg2")])]
+        tickets = []
+        results = {}
+        for i, (text, off) in enumerate(batches):
+            tickets.append(q.submit(text, off))
+            if i >= 1:                           # depth 2: wait for the batch before the previous one
+                results[i - 1] = q.wait(tickets[i - 1])
+        results[len(batches) - 1] = q.wait(tickets[-1])
+        for i, (text, off) in enumerate(batches):
+            o_off, o_tok, o_cost, _ = oracle_tok.tokenize_batch(text, off, threads=8)
+            assert_batch_equal(results[i], o_off, o_tok, o_cost)
+        import kanpyo_b200
+        with pytest.raises(kanpyo_b200.KanpyoB200Error):      # a ticket never issued
+            q.wait_raw(99)
+    finally:
+        q.close()
+
+
+@pytest.mark.parametrize("all_devices", [False, True])
+def test_shards_single_process(gpu_ipadic, oracle_tok, vocab, all_devices):
+    """kp_shards_*: byte-balanced sentence ranges over the GPUs of one process; the host result lands at global
+    offsets, the gathered result on devices[0].  With one device the same code runs without NCCL; with all
+    devices (skipped below two) the dictionary travels by ncclBroadcast and the tokens by ncclSend / ncclRecv."""
+    import torch
+    from kanpyo_b200 import corpus, sharded
+    n = torch.cuda.device_count()
+    if all_devices and n < 2:
+        pytest.skip("needs at least two GPUs")
+    sh = sharded.Shards(gpu_ipadic, devices=list(range(n)) if all_devices else [0])
+    try:
+        for kind, ns in (("cfg2", 5000), ("cfg3", 37), ("cfg2", 1)):
+            text, off = corpus.synth_corpus(vocab, ns, kind, seed=5)
+            o_off, o_tok, o_cost, _ = oracle_tok.tokenize_batch(text, off, threads=8)
+            assert_batch_equal(sh.tokenize(text, off), o_off, o_tok, o_cost)
+            assert_batch_equal(sh.tokenize_gather(text, off), o_off, o_tok, o_cost)
+        tm = sh.times()
+        assert tm["call_ms"] > 0 and (tm["dict_broadcast_ms"] > 0) == (all_devices and n > 1)
+        res = sh.tokenize(b"", np.zeros(1, np.uint64))
+        assert len(res.tokens) == 0 and res.tok_off.tolist() == [0]
+    finally:
+        sh.close()
+
+
+def test_two_tokenizers_share_one_dict(gpu_ipadic, oracle_tok, vocab):
+    """A Dict keeps one handle per device for its whole life: building further tokenizers, queues or a
+    sharded group on it never invalidates a live tokenizer."""
+    import kanpyo_b200
+    from kanpyo_b200 import corpus
+    from kanpyo_b200.tokenizer import Queue
+    text, off = corpus.synth_corpus(vocab, 400, "cfg2", seed=3)
+    o = oracle_tok.tokenize_batch(text, off)
+    a = kanpyo_b200.Tokenizer(gpu_ipadic, device=0)
+    b = kanpyo_b200.Tokenizer(gpu_ipadic, device=0)
+    q = Queue(gpu_ipadic, device=0, depth=1)
+    assert_batch_equal(a.tokenize_batch_bytes(text, off), o[0], o[1], o[2])
+    b.close()
+    q.close()
+    assert_batch_equal(a.tokenize_batch_bytes(text, off), o[0], o[1], o[2])
+    a.close()
+
+
+# ---- SURVEY 8f rows through the CUDA path -------------------------------------------------------------------
+def test_dict_container_to_gpu_tokens(gpu_ipadic, oracle_tok, vocab, tmp_path):
+    """`.dict` zip container (kanpyo-dict/src/dict.rs:51-116): Dict.build -> Dict.load -> Tokenizer on the GPU ->
+    the oracle's tokens and feature strings."""
+    import kanpyo_b200
+    from kanpyo_b200 import corpus
+    from test_oracle_pins import README
+    path = str(tmp_path / "ipadic.dict")
+    with open(path, "wb") as f:
+        gpu_ipadic.build(f)
+    with open(path, "rb") as f:
+        loaded = kanpyo_b200.Dict.load(f)
+    t = kanpyo_b200.Tokenizer(loaded, device=0)
+    try:
+        text, off = corpus.synth_corpus(vocab, 2000, "cfg3", seed=9)
+        o_off, o_tok, o_cost, _ = oracle_tok.tokenize_batch(text, off, threads=8)
+        assert_batch_equal(t.tokenize_batch_bytes(text, off), o_off, o_tok, o_cost)
+        for s, expect in README.items():
+            assert t.format_tokens(t.tokenize(s)) == "".join("%s\t%s\n" % (a, b) for a, b in expect)
+    finally:
+        t.close()
+
+
+def test_graphviz_matches_oracle(gpu_tok, oracle_tok):
+    """Dot text of the device lattice == the oracle's restatement of src/graphviz.rs over the oracle's lattice,
+    byte for byte, in both views."""
+    from kanpyo_b200.graphviz import graphviz
+    from oracle import graphviz as ograph
+    for s in ["すもももももももものうち", "Tシャツを3枚買ったABC", "", "東京都に住んでいます。", "\U0001F600の犬", "カタカナ語"]:
+        for full in (False, True):
+            assert graphviz(gpu_tok, s, dpi=72, full_state=full) == ograph.graphviz(oracle_tok, s, 72, full), (s, full)

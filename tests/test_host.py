@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, n), "libkanpyo_b200.so does not export %s" % n
         assert n in _lib.SYMBOLS, "ctypes binding misses %s" % n
     assert sorted(_lib.SYMBOLS) == names, "binding declares symbols the header does not"
-    assert L.kp_abi_version() == 1
+    assert L.kp_abi_version() == 2
     assert L.kp_strerror(-2).decode().startswith("CUDA error or no usable device")
 
 
@@ -283,9 +283,8 @@ import torch
 import torch.distributed as dist
 sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
 from kanpyo_b200 import sharded, corpus
-from kanpyo_b200.tokenizer import TOKEN_DTYPE
 from oracle import oracle
-from helpers import reference_fixture_dict, to_product_dict
+from helpers import oracle_to_token8, reference_fixture_dict, to_product_dict
 
 dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
 rank, world = dist.get_rank(), dist.get_world_size()
@@ -303,26 +302,34 @@ text = np.frombuffer(b"".join(blobs), np.uint8)
 otk = oracle.OracleTokenizer(od)
 s0, s1 = corpus.shard_by_bytes(off, world)[rank]
 l_off, l_tok, l_cost, _ = otk.tokenize_batch(text, off[s0:s1 + 1])
-rec = np.zeros(len(l_tok), TOKEN_DTYPE)
-rec["id"], rec["cls"], rec["position"], rec["start"] = l_tok[:, 0], l_tok[:, 1], l_tok[:, 2], l_tok[:, 3]
-rec["char_len"] = l_tok[:, 4] - l_tok[:, 3]
-g = sharded.gather_results(torch.from_numpy(l_off.view(np.int64).copy()), torch.from_numpy(rec.view(np.uint8).copy()),
-                           torch.from_numpy(l_cost.copy()))
+rec = oracle_to_token8(l_tok)
+ranges = corpus.shard_by_bytes(off, world)
+tg = sharded.TokenGather("cpu", max(b - a for a, b in ranges), 64, 0)
+def u8(a):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).copy())
+for _ in range(2):      # the buffers are reused across calls
+    g = tg.gather(u8(l_off.astype(np.uint32)), u8(rec), u8(l_cost))
 if rank == 0:
-    res = sharded.to_batch_result(*g)
+    res = sharded.to_batch_result(*g, off)
     f_off, f_tok, f_cost, _ = otk.tokenize_batch(text, off)
     assert np.array_equal(res.tok_off, f_off), (res.tok_off, f_off)
     assert np.array_equal(res.eos_cost, f_cost)
     assert np.array_equal(res.tokens["id"].astype(np.int64), f_tok[:, 0])
+    assert np.array_equal(res.tokens["cls"].astype(np.int64), f_tok[:, 1])
     assert np.array_equal(res.tokens["position"].astype(np.int64), f_tok[:, 2])
+    assert np.array_equal(res.tokens["start"].astype(np.int64), f_tok[:, 3])
     assert np.array_equal(res.tokens["start"].astype(np.int64) + res.tokens["char_len"], f_tok[:, 4])
 else:
     assert g is None
-# 3. an empty shard still takes part
-e = sharded.gather_results(torch.zeros(1, dtype=torch.int64), torch.zeros(0, dtype=torch.uint8),
-                           torch.zeros(0, dtype=torch.int32))
+# 3. an empty shard still takes part; a shard beyond the capacity raises instead of truncating
+e = tg.gather(u8(np.zeros(1, np.uint32)), torch.zeros(0, dtype=torch.uint8), torch.zeros(0, dtype=torch.uint8))
 if rank == 0:
-    assert e[0].tolist() == [0] and e[1].numel() == 0
+    assert e[0].tolist() == [0] and e[1].numel() == 0 and e[2].numel() == 0
+try:
+    tg.gather(u8(np.zeros(2, np.uint32)), torch.zeros(8 * 65, dtype=torch.uint8), torch.zeros(4, dtype=torch.uint8))
+    raise SystemExit("capacity overflow not detected")
+except ValueError:
+    pass
 dist.barrier()
 dist.destroy_process_group()
 print("worker", rank, "ok")
@@ -410,3 +417,60 @@ def test_dict_container_round_trip_and_known_bytes(tmp_path, oracle_mod):
 
 Dict_FIELDS = ("da", "dup_ids", "dup_counts", "morphs", "conn", "char_category", "invoke_list", "group_list", "unk_cat",
                "unk_first_id", "unk_count", "unk_morphs")
+
+
+def test_expand_tokens8_rebuilds_positions(oracle_mod, oracle_tok, vocab):
+    """kp_token8 -> kp_token on the host (C helper and its numpy mirror): positions / starts are rebuilt
+    backwards from each sentence's EOS record, also for truncated paths (first token not at byte 0) and
+    empty paths (no token at all)."""
+    from kanpyo_b200 import _lib, corpus
+    from kanpyo_b200.tokenizer import TOKEN_DTYPE, expand_tokens8
+    from helpers import oracle_to_token8, pack
+    cases = []
+    text, off = corpus.synth_corpus(vocab, 300, "cfg3")
+    cases.append((oracle_tok, text, off))
+    fx = oracle_mod.OracleTokenizer(reference_fixture_dict(oracle_mod))
+    text, off = pack(["テスト", "", "xテスト", "テストx", "xx", "テxスト", "あいうえお", "x"])
+    cases.append((fx, text, off))
+    L = _lib.load()
+    for tk, text, off in cases:
+        o_off, o_tok, _, _ = tk.tokenize_batch(text, off)
+        t8 = oracle_to_token8(o_tok)
+        full = expand_tokens8(o_off, t8, off)
+        assert np.array_equal(full["id"].astype(np.int64), o_tok[:, 0])
+        assert np.array_equal(full["cls"].astype(np.int64), o_tok[:, 1])
+        assert np.array_equal(full["position"].astype(np.int64), o_tok[:, 2])
+        assert np.array_equal(full["start"].astype(np.int64), o_tok[:, 3])
+        assert np.array_equal(full["start"].astype(np.int64) + full["char_len"], o_tok[:, 4])
+        off32 = np.ascontiguousarray(o_off, np.uint32)
+        off64 = np.ascontiguousarray(off, np.uint64)
+        r = _lib.Result8(n_sent=len(off) - 1, n_tokens=len(t8), tok_off=off32.ctypes.data, tokens=t8.ctypes.data,
+                         eos_cost=None)
+        out = np.zeros(len(t8), TOKEN_DTYPE)
+        _lib.check(L.kp_expand_tokens8(C.byref(r), off64.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+        assert np.array_equal(out, full)
+    assert any((np.diff(o_off) == 0).any() for _ in [0])      # the fixture batch holds empty paths
+
+
+def test_blob_is_refused_unless_it_is_what_pack_wrote(oracle_mod):
+    """kp_dict_create_from_blob validates before it touches a device: a flipped payload byte,
+    a truncated blob, a section pointing outside the blob or a stale layout version all give KP_ERR_BLOB."""
+    from kanpyo_b200 import _lib
+    L = _lib.load()
+    blob = to_product_dict(reference_fixture_dict(oracle_mod)).pack()
+
+    def status(b):
+        h = C.c_void_p()
+        buf = np.ascontiguousarray(b)
+        return L.kp_dict_create_from_blob(buf.ctypes.data_as(C.c_void_p), buf.size, 0, C.byref(h))
+
+    good = status(blob)
+    assert good in (0, -2), good                  # OK on a GPU box; "no device" here -- but never KP_ERR_BLOB
+    bad = blob.copy(); bad[len(bad) // 2] ^= 1
+    assert status(bad) == -7
+    assert status(blob[:len(blob) - 256]) == -7
+    hdr = blob.copy().view(np.uint64)
+    hdr[9] = len(blob) + 256                      # off_da beyond the blob
+    assert status(hdr.view(np.uint8)) == -7
+    ver = blob.copy(); ver[8] = 1                 # layout version 1 (round 1) is not accepted
+    assert status(ver) == -7

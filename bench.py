@@ -401,14 +401,22 @@ def product_arm(args):
     # step's H2D and D2H are inside the timed region, overlapped with the kernels of the neighbouring steps
     q = Queue(d, device=local, depth=args.queue_depth)
 
-    def run_queue(k):
-        tks = [q.submit_ptr(h_text.data_ptr(), h_off.data_ptr(), S) for _ in range(k)]
-        return [q.wait_raw(t) for t in tks][-1]
+    def run_queue(qq, k, text_ptr, off_ptr, ns):
+        """k steps through the queue, `depth` in flight: submit step i + depth only after step i was waited for
+        (its result buffers are the ones step i + depth reuses)."""
+        pending, last = [], None
+        for _ in range(k):
+            if len(pending) == qq.depth:
+                last = qq.wait_raw(pending.pop(0))
+            pending.append(qq.submit_ptr(text_ptr, off_ptr, ns))
+        for t in pending:
+            last = qq.wait_raw(t)
+        return last
 
-    run_queue(max(args.warmup, 2 * args.queue_depth))
+    run_queue(q, max(args.warmup, 2 * args.queue_depth), h_text.data_ptr(), h_off.data_ptr(), S)
     barrier()
     t0 = time.perf_counter()
-    r_e2e = run_queue(args.steps)
+    r_e2e = run_queue(q, args.steps, h_text.data_ptr(), h_off.data_ptr(), S)
     torch.cuda.synchronize()
     e2e_total_s = time.perf_counter() - t0
     barrier()
@@ -469,13 +477,10 @@ def product_arm(args):
         barrier()
         # e2e of the strong split: each rank's queue on its shard, host buffers in and out
         q2 = Queue(d, device=local, depth=args.queue_depth)
-        for _ in range(2 * args.queue_depth):
-            q2.wait_raw(q2.submit_ptr(hs_text.data_ptr(), hs_off.data_ptr(), Ss))
+        run_queue(q2, 2 * args.queue_depth, hs_text.data_ptr(), hs_off.data_ptr(), Ss)
         barrier()
         t0 = time.perf_counter()
-        tks = [q2.submit_ptr(hs_text.data_ptr(), hs_off.data_ptr(), Ss) for _ in range(args.steps)]
-        for t in tks:
-            q2.wait_raw(t)
+        run_queue(q2, args.steps, hs_text.data_ptr(), hs_off.data_ptr(), Ss)
         strong_e2e_s = time.perf_counter() - t0
         barrier()
         q2.close()

@@ -410,6 +410,7 @@ extern "C" int kp_shards_create(const kp_dict_arrays* arrays, const int* devices
 
 extern "C" void kp_shards_destroy(kp_shards* g) {
     if (!g) return;
+    const int dev0 = g->dev.empty() ? -1 : g->dev[0]->device;
     for (kp_shard_dev* d : g->dev) {
         if (d->worker.th.joinable()) {
             d->worker.wait();
@@ -424,7 +425,7 @@ extern "C" void kp_shards_destroy(kp_shards* g) {
         if (d->dict) kp_dict_destroy(d->dict);
         delete d;
     }
-    if (!g->dev.empty()) cudaSetDevice(g->dev.empty() ? 0 : g->dev[0]->device);
+    if (dev0 >= 0) cudaSetDevice(dev0);        // the gathered result lives on devices[0]
     g->g_tok_off.release();
     g->g_tokens.release();
     g->g_eos.release();

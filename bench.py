@@ -400,6 +400,7 @@ def product_arm(args):
     # ---- e2e: the asynchronous queue (kp_queue_*), pinned HOST buffers in, pinned HOST result out; every
     # step's H2D and D2H are inside the timed region, overlapped with the kernels of the neighbouring steps
     q = Queue(d, device=local, depth=args.queue_depth)
+    q.set_path(args.path)
 
     def run_queue(qq, k, text_ptr, off_ptr, ns):
         """k steps through the queue, `depth` in flight: submit step i + depth only after step i was waited for
@@ -477,6 +478,7 @@ def product_arm(args):
         barrier()
         # e2e of the strong split: each rank's queue on its shard, host buffers in and out
         q2 = Queue(d, device=local, depth=args.queue_depth)
+        q2.set_path(args.path)
         run_queue(q2, 2 * args.queue_depth, hs_text.data_ptr(), hs_off.data_ptr(), Ss)
         barrier()
         t0 = time.perf_counter()

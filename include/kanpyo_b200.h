@@ -219,6 +219,7 @@ int kp_tokenizer_set_path(kp_tokenizer* t, int path);
  * with the copies of one batch hidden behind the kernels of its neighbours. */
 typedef struct kp_queue kp_queue;
 int kp_queue_create(const kp_dict* d, uint32_t depth, kp_queue** out);
+int kp_queue_set_path(kp_queue* q, int path);    /* kp_tokenizer_set_path on every context */
 int kp_queue_submit(kp_queue* q, const uint8_t* utf8, const uint64_t* offsets, uint64_t n_sent, uint64_t* ticket);
 int kp_queue_wait(kp_queue* q, uint64_t ticket, kp_result8* out);
 void kp_queue_destroy(kp_queue* q);

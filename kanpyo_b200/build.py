@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "libkanpyo_b200.so")
 # tuning experiments: KP_VARIANT=name KP_DEFINES="-DKP_X=1 ..." python -m kanpyo_b200.build builds
 # kanpyo_b200/_variants/libkanpyo_b200.<name>.so; KANPYO_B200_LIB=<path> makes _lib.load() use it.
 VARIANT_DIR = os.path.join(HERE, "_variants")
-SOURCES = ["kp_dict.cu", "kp_kernels.cu", "kp_api.cu", "kp_queue.cu", "kp_dictbuild.cpp"]
+SOURCES = ["kp_dict.cu", "kp_kernels.cu", "kp_fused.cu", "kp_api.cu", "kp_queue.cu", "kp_dictbuild.cpp"]
 HEADERS = ["kp_common.cuh", "kp_kernels.cuh", os.path.join("..", "..", "include", "kanpyo_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-Xptxas", "-v", "-shared", "-cudart", "static", "-ldl", "-lpthread"]

@@ -74,7 +74,10 @@ struct PinBuf {   // pinned host memory, preserved on growth
 };
 
 constexpr uint32_t KP_PERM_REFRESH = 16;
-enum { EV_START, EV_H2D, EV_PREP, EV_LATTICE, EV_BUCKET, EV_VITERBI, EV_BACKTRACE, EV_PACK, EV_FUSED0, EV_FUSED1, EV_END, EV_COUNT };
+#ifndef KP_FUSED_BYTES
+#define KP_FUSED_BYTES 192, 256, 320, 448, 768, 1536     // byte limits of the fused kernel's size classes
+#endif
+enum { EV_START, EV_H2D, EV_PIPE0, EV_PREP, EV_LATTICE, EV_BUCKET, EV_VITERBI, EV_BACKTRACE, EV_PACK, EV_FUSED0, EV_FUSED1, EV_END, EV_COUNT };
 
 }  // namespace
 
@@ -86,6 +89,11 @@ struct kp_tokenizer {
     uint64_t chunk_bytes = 64ull << 20;
     bool count_work = false;
     int path_mode = KP_PATH_AUTO;
+    bool fused_ok = false;             // the dictionary fits the fused kernel's packed records
+    kp_fused_classes fclasses = {};
+    cudaStream_t fstream[KP_FUSED_MAX_CLASSES] = {};
+    cudaEvent_t fev_fork = nullptr, fev_join[KP_FUSED_MAX_CLASSES] = {};
+    DevBuf flists, fctl;
     kp_perm perm = {};
     uint32_t perm_age = 0;     // passes since the column order was last ranked
     DevBuf perm_hist, perm_map, perm_conn;
@@ -140,9 +148,9 @@ int run_pipeline(kp_tokenizer* t, kp_chunk& c, StageTimes* times) {
     c.coff = t->coff.as<uint32_t>();
     c.scan_tmp = t->scan_tmp.as<uint64_t>();
     uint64_t* h_tot = t->h_totals.as<uint64_t>();
-    uint32_t* h_err = (uint32_t*)(h_tot + 8);
+    uint32_t* h_err = (uint32_t*)(h_tot + 16);
 
-    KP_CUDA(cudaEventRecord(t->ev[EV_H2D], st));
+    KP_CUDA(cudaEventRecord(t->ev[EV_PIPE0], st));
     KP_CUDA(cudaMemsetAsync(c.lenhist, 0, sizeof(uint32_t) * kp_len_bins(), st));
     KP_LAUNCH(kp_launch_prep_count(c, st));
     KP_LAUNCH(kp_launch_scan(c.nchar, c.coff, S, c.scan_tmp, &c.totals[0], st));
@@ -232,6 +240,57 @@ int run_pipeline(kp_tokenizer* t, kp_chunk& c, StageTimes* times) {
     return KP_OK;
 }
 
+// The fused per-sentence kernel over the chunk: classify by sentence bytes, one persistent launch per size
+// class (largest first, each on its own stream so that the tail of one class overlaps the start of the
+// next), then the flags and the list of sentences left to the pipeline come back in one round trip.
+int run_fused(kp_tokenizer* t, kp_chunk& c, uint32_t* left) {
+    cudaStream_t st = t->stream;
+    const kp_ddict& d = t->dict->view;
+    const uint32_t S = c.S_all, nc = t->fclasses.n;
+    // fctl: [0..nc) list lengths, [8..8+nc) tickets, [16] sentences left to the pipeline
+    KP_TRY(t->sel.ensure(sizeof(uint32_t) * (S + 1)));
+    KP_TRY(t->flists.ensure(sizeof(uint32_t) * ((size_t)nc * S + 1)));
+    KP_TRY(t->fctl.ensure(sizeof(uint32_t) * 32));
+    c.sel_out = t->sel.as<uint32_t>();
+    uint32_t* fctl = t->fctl.as<uint32_t>();
+    uint64_t* h_tot = t->h_totals.as<uint64_t>();
+    uint32_t* h_err = (uint32_t*)(h_tot + 16);
+    uint32_t* h_ctl = h_err + 4;
+    KP_CUDA(cudaMemsetAsync(fctl, 0, sizeof(uint32_t) * 32, st));
+    KP_CUDA(cudaEventRecord(t->ev[EV_FUSED0], st));
+    KP_LAUNCH(kp_launch_fused_classify(c, t->fclasses, t->flists.as<uint32_t>(), fctl, fctl + 16, st));
+    KP_CUDA(cudaEventRecord(t->fev_fork, st));
+    for (uint32_t i = 0; i < nc; i++) {
+        const uint32_t k = nc - 1 - i;               // largest sentences first
+        KP_CUDA(cudaStreamWaitEvent(t->fstream[k], t->fev_fork, 0));
+        KP_LAUNCH(kp_launch_fused(c, d, t->fclasses.c[k], t->flists.as<uint32_t>() + (size_t)k * S, fctl + k, fctl + 8 + k,
+                                  fctl + 16, S, t->fstream[k]));
+        KP_CUDA(cudaEventRecord(t->fev_join[k], t->fstream[k]));
+        KP_CUDA(cudaStreamWaitEvent(st, t->fev_join[k], 0));
+    }
+    KP_CUDA(cudaEventRecord(t->ev[EV_FUSED1], st));
+    KP_CUDA(cudaMemcpyAsync(h_err, c.err, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaMemcpyAsync(h_ctl, fctl, sizeof(uint32_t) * 32, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaMemcpyAsync(h_tot + 8, c.totals + 8, sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaStreamSynchronize(st));
+    if (h_err[1]) {
+        kp_set_error("sentence offsets are not ascending or exceed the text length");
+        return KP_ERR_ARG;
+    }
+    if (h_err[0]) {
+        kp_set_error("input contains invalid UTF-8");
+        return KP_ERR_UTF8;
+    }
+    *left = h_ctl[16];
+    t->counters.chars += h_tot[8];
+    t->counters.nodes += h_tot[9];
+    t->profile.fused_sentences += (uint32_t)h_tot[10];
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t->ev[EV_FUSED0], t->ev[EV_FUSED1]);
+    t->profile.fused_ms += ms;
+    return KP_OK;
+}
+
 // One device pass over a chunk whose text / offsets are already in device memory, in two halves so
 // that a multi-GPU caller can learn every shard's token count before any shard packs its result:
 //   chunk_compute  lattice, Viterbi, back-trace; tokens staged; token counts scanned; *n_tokens read back
@@ -241,9 +300,9 @@ int chunk_compute(kp_tokenizer* t, kp_chunk& c, uint64_t* n_tokens, StageTimes* 
     const uint32_t S = c.S;
     c.S_all = S;
     c.sel = nullptr;
-    KP_TRY(t->totals.ensure(sizeof(uint64_t) * 8));
+    KP_TRY(t->totals.ensure(sizeof(uint64_t) * 16));
     KP_TRY(t->err.ensure(sizeof(uint32_t) * 4));
-    KP_TRY(t->h_totals.ensure(sizeof(uint64_t) * 16, 0));
+    KP_TRY(t->h_totals.ensure(sizeof(uint64_t) * 40, 0));
     KP_TRY(t->tcount.ensure(sizeof(uint32_t) * (S + 1)));
     KP_TRY(t->toff32.ensure(sizeof(uint32_t) * (S + 2)));
     KP_TRY(t->stage.ensure(sizeof(kp_token) * ((size_t)c.B + S + 2)));
@@ -255,10 +314,22 @@ int chunk_compute(kp_tokenizer* t, kp_chunk& c, uint64_t* n_tokens, StageTimes* 
     c.stage = t->stage.as<kp_token>();
     c.scan_tmp = t->scan_tmp.as<uint64_t>();
     uint64_t* h_tot = t->h_totals.as<uint64_t>();
-    KP_CUDA(cudaMemsetAsync(c.totals, 0, sizeof(uint64_t) * 8, st));
+    KP_CUDA(cudaEventRecord(t->ev[EV_H2D], st));          // the inputs are on the device from here on
+    KP_CUDA(cudaMemsetAsync(c.totals, 0, sizeof(uint64_t) * 16, st));
     KP_CUDA(cudaMemsetAsync(c.err, 0, sizeof(uint32_t) * 4, st));
     t->pipeline_timed = false;
-    KP_TRY(run_pipeline(t, c, times));
+    if (t->fused_ok && t->path_mode != KP_PATH_PIPELINE && !t->count_work && S > 0) {
+        // fused per-sentence kernel first; the pipeline then takes the sentences it left (c.sel)
+        uint32_t left = 0;
+        KP_TRY(run_fused(t, c, &left));
+        if (left) {
+            c.sel = t->sel.as<uint32_t>();
+            c.S = left;
+            KP_TRY(run_pipeline(t, c, times));
+        }
+    } else {
+        KP_TRY(run_pipeline(t, c, times));
+    }
     c.scan_tmp = t->scan_tmp.as<uint64_t>();
     KP_LAUNCH(kp_launch_scan(c.tcount, c.toff32, c.S_all, c.scan_tmp, &c.totals[3], st));
     KP_CUDA(cudaMemcpyAsync(h_tot, c.totals, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, st));
@@ -272,7 +343,7 @@ int chunk_compute(kp_tokenizer* t, kp_chunk& c, uint64_t* n_tokens, StageTimes* 
     t->counters.pairs += h_tot[6];
     if (times && t->pipeline_timed) {
         float ms = 0;
-        cudaEventElapsedTime(&ms, t->ev[EV_H2D], t->ev[EV_PREP]);       times->prep += ms;
+        cudaEventElapsedTime(&ms, t->ev[EV_PIPE0], t->ev[EV_PREP]);     times->prep += ms;
         cudaEventElapsedTime(&ms, t->ev[EV_PREP], t->ev[EV_LATTICE]);   times->lattice += ms;
         cudaEventElapsedTime(&ms, t->ev[EV_LATTICE], t->ev[EV_BUCKET]); times->bucket += ms;
         cudaEventElapsedTime(&ms, t->ev[EV_BUCKET], t->ev[EV_VITERBI]); times->viterbi += ms;
@@ -337,6 +408,37 @@ extern "C" int kp_tokenizer_create(const kp_dict* d, kp_tokenizer** out) {
         t->perm.connP = t->perm_conn.as<int16_t>();
         cudaMemset(t->perm.connP, 0, sizeof(int16_t) * (size_t)v.conn_row * v.connT_stride);   // row padding
     }
+    {   // fused per-sentence path: size classes by sentence bytes (measured on the synthetic corpora: 0.34-0.43
+        // chars, <= 1.6 known nodes and <= 1.8 reduced slots per byte at the 99th percentile; what does not fit
+        // its class goes to the pipeline)
+        const kp_blob_header* h = (const kp_blob_header*)d->host_blob.data();
+        t->fused_ok = kp_fused_dict_ok(d->view, (const kp_catinfo*)(d->host_blob.data() + h->off_catinfo));
+        static const uint32_t limits[] = {KP_FUSED_BYTES};
+        t->fclasses.n = 0;
+        for (uint32_t lim : limits) {
+            if (t->fclasses.n >= KP_FUSED_MAX_CLASSES) break;
+            kp_fused_class& k = t->fclasses.c[t->fclasses.n++];
+            k.max_bytes = lim;
+            k.cap_c = std::min<uint32_t>(lim * 9 / 20 + 8, 1020);
+            k.cap_k = std::min<uint32_t>((lim * 17 / 10 + 32) & ~1u, 4000);
+            k.cap_r = std::min<uint32_t>(lim * 19 / 10 + 48, 4090);
+            if (k.cap_k * 3 < 8 * (k.cap_c + 1)) k.cap_k = ((8 * (k.cap_c + 1) + 2) / 3 + 1) & ~1u;   // the path overlays t_slot | hy
+            if (k.cap_r < k.cap_k / 2) k.cap_r = k.cap_k / 2;                                           // the hits overlay k_dp
+        }
+        if (t->fused_ok) {
+            int rc = kp_fused_prepare(&t->fclasses, t->device);
+            cudaError_t e2 = cudaEventCreateWithFlags(&t->fev_fork, cudaEventDisableTiming);
+            for (uint32_t k = 0; k < t->fclasses.n && e2 == cudaSuccess; k++) {
+                e2 = cudaStreamCreateWithFlags(&t->fstream[k], cudaStreamNonBlocking);
+                if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&t->fev_join[k], cudaEventDisableTiming);
+            }
+            if (rc || e2 != cudaSuccess) {
+                if (!rc) kp_set_error("fused path: stream/event creation failed: %s", cudaGetErrorString(e2));
+                kp_tokenizer_destroy(t);
+                return rc ? rc : KP_ERR_CUDA;
+            }
+        }
+    }
     *out = t;
     return KP_OK;
 }
@@ -347,13 +449,18 @@ extern "C" void kp_tokenizer_destroy(kp_tokenizer* t) {
     if (t->stream) cudaStreamSynchronize(t->stream);
     DevBuf* bufs[] = {&t->text, &t->off, &t->nchar, &t->coff, &t->binfo, &t->ncount, &t->noff, &t->bcount, &t->boff,
                       &t->bfill, &t->ucount, &t->rbk, &t->nhit, &t->hits, &t->rec, &t->tgt, &t->red, &t->ndp, &t->bnode, &t->path, &t->pre, &t->lenhist, &t->order, &t->tcount, &t->toff32,
-                      &t->scan_tmp, &t->totals, &t->err, &t->stage, &t->sel, &t->d_tok_off, &t->d_tokens, &t->d_eos, &t->perm_hist, &t->perm_map,
+                      &t->scan_tmp, &t->totals, &t->err, &t->stage, &t->sel, &t->flists, &t->fctl, &t->d_tok_off, &t->d_tokens, &t->d_eos, &t->perm_hist, &t->perm_map,
                       &t->perm_conn};
     for (DevBuf* b : bufs) b->release();
     PinBuf* pins[] = {&t->h_totals, &t->h_tok_off, &t->h_tokens, &t->h_eos, &t->h_misc};
     for (PinBuf* b : pins) b->release();
     for (int i = 0; i < EV_COUNT; i++)
         if (t->ev[i]) cudaEventDestroy(t->ev[i]);
+    if (t->fev_fork) cudaEventDestroy(t->fev_fork);
+    for (uint32_t k = 0; k < KP_FUSED_MAX_CLASSES; k++) {
+        if (t->fev_join[k]) cudaEventDestroy(t->fev_join[k]);
+        if (t->fstream[k]) cudaStreamDestroy(t->fstream[k]);
+    }
     if (t->stream) cudaStreamDestroy(t->stream);
     delete t;
 }
@@ -656,7 +763,11 @@ extern "C" int kp_tokenize(kp_tokenizer* t, const uint8_t* utf8, uint64_t len, k
 extern "C" int kp_lattice_dump(kp_tokenizer* t, const uint8_t* utf8, uint64_t len, kp_lattice* out) {
     if (!t || !out || (len && !utf8)) return KP_ERR_ARG;
     kp_result r;
-    KP_TRY(kp_tokenize(t, utf8, len, &r));
+    const int mode = t->path_mode;
+    t->path_mode = KP_PATH_PIPELINE;          // the node table exists only in the pipeline's scratch
+    const int rc_tok = kp_tokenize(t, utf8, len, &r);
+    t->path_mode = mode;
+    KP_TRY(rc_tok);
     // scratch of the (single-chunk) pass is still intact
     const uint32_t N = (uint32_t)(t->counters.nodes - 1);   // device nodes (no BOS)
     const uint32_t NB = (uint32_t)t->counters.chars + 1;

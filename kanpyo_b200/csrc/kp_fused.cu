@@ -1,0 +1,674 @@
+// kp_fused.cu — the whole path of one sentence in one warp, on chip.
+//
+// The multi-kernel pipeline (kp_kernels.cu) moves ~250 bytes of scratch per input byte through HBM and
+// every one of its kernels waits on dependent gathers into that scratch.  A sentence of the sizes real
+// text has (BASELINE.json configs[1]: 82 chars, ~270 dictionary nodes, ~30 tokens) fits in a few KB, so
+// here ONE WARP owns a sentence from its bytes to its tokens and keeps the lattice in shared memory:
+//
+//   decode    UTF-8 check, char offsets, classes, unknown-run ends            lattice.rs:105-111, 55-84
+//   walk      lane = start position: double-array walk, hits {id, start, chars} da.rs:155-182
+//   count     duplicates per hit, nodes per start / per end, scans            index.rs:40-53
+//   expand    node {left, cost, id} at its start, {right} at its end bucket    lattice.rs:156-201
+//   sweep     boundary by boundary: lanes = (target x predecessor slice),      lattice.rs:116-143
+//             DPX add-min per pair, xor-shuffle min across the slices          connection.rs:12-14
+//   trace     from EOS: first predecessor attaining dp (list order)           lattice.rs:136-153
+//   tokens    staged at the sentence's slot of the staging area               tokenizer.rs:22-43
+//
+// Only the dictionary (L2-resident) and the sentence's own bytes are read from global memory; only the
+// tokens, the token count and dp[EOS] are written.  Sentences that do not fit the launch's capacities
+// (chars, nodes, hits) are appended to a list and taken by the pipeline afterwards: results are
+// identical either way (tests/test_gpu_parity.py runs both).
+//
+// Exactness notes
+//   * Unknown nodes are not materialised.  Every start inside a same-class run emits the class's unknown
+//     ids and they all end at the run's end; a successor only ever needs min(dp) per id, so each (end, id)
+//     has ONE slot, min-merged in start order with a strict '<' (the first minimal start is kept).  The
+//     minimum VALUE a successor sees is unchanged (the pipeline's reduced buckets do the same).
+//   * The reference keeps the FIRST predecessor attaining the minimum in `edges[p]` order, which is
+//     insertion order: ascending start, known before unknown, ascending id (two nodes of one bucket with
+//     the same start have the same length, hence come from the same trie hit or the same class).  Bucket
+//     slots are handed out by atomics here, so the back-trace compares the key (start, kind, id) instead
+//     of the slot index: same winner.
+//   * dp arithmetic is the reference's: dp = min(min_j(dp_j + conn) + cost, INF), BOS = 0, a node without
+//     predecessor (or with dead ones only) keeps INF and cuts the path.
+#include <limits.h>
+
+#include "kp_kernels.cuh"
+
+#define KP_FULL 0xFFFFFFFFu
+
+namespace {
+
+constexpr uint32_t NONE16 = 0xFFFFu;
+constexpr uint32_t ID_BITS = 20, ID_MASK20 = (1u << ID_BITS) - 1;   // ids the packed records can carry
+constexpr uint32_t MAX_K = 2047;          // duplicates + 1 per hit
+constexpr uint32_t MAX_NCH = 63;          // chars of a dictionary word
+constexpr uint32_t EOS_INFO = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+__device__ __forceinline__ bool is_cont(uint32_t c) { return (c & 0xC0u) == 0x80u; }
+__device__ __forceinline__ uint32_t lead_len(uint32_t c) {  // 0 = not a valid lead byte
+    if (c < 0x80u) return 1;
+    if (c >= 0xC2u && c <= 0xDFu) return 2;
+    if (c >= 0xE0u && c <= 0xEFu) return 3;
+    if (c >= 0xF0u && c <= 0xF4u) return 4;
+    return 0;
+}
+__device__ __forceinline__ uint2 ld_morph(const short4* __restrict__ m, uint32_t i) {   // {left | right << 16, cost}
+    return __ldg((const uint2*)m + i);
+}
+__device__ __forceinline__ int ld_cell(const int16_t* __restrict__ connT, uint32_t right, uint32_t stride, uint32_t left) {
+    return (int)__ldg(connT + (size_t)right * stride + left);
+}
+
+}  // namespace
+
+// Shared-memory layout of one warp's sentence (byte offsets).  C1 = cap_c + 2 boundary entries.
+//   nstart  u32[C1]   known nodes starting at p: count -> first index -> (after expand) END index
+//   bstart  u32[C1]   reduced-bucket size of boundary e -> first slot (bstart[n+1] = slots in use)
+//   bcur    u32[C1]   known nodes ending at e (| bit 31: an unknown node ends here) -> fill cursor ->
+//                     (after expand) first SHARED slot of bucket e
+//   binfo   u32[C1]   per start: unknown end (10) | emits unknown << 10 | class unk_count (5) << 11 | unk_first << 16
+//   bpos    u16[C1]   byte offset of char p inside the sentence (bpos[n] = bytes)
+//   bcls    u8 [C1]   class of char p
+//   t_lc    u32[K]    known node: left | cost << 16                      (K = cap_k, index = node)
+//   t_info  u32[K]    known node: id | chars << 20; EOS_INFO for the EOS node
+//   t_slot  u16[K]    known node: its slot in the bucket of its end      } the path {id|kind<<30, start|chars<<16}
+//   hy      u16[K/2]  hit: start (10) | chars (6) << 10                   } overlays these two after the sweep
+//   k_dp    i32[R]    bucket slot: dp (hx u32[K/2]: hit id | k << 20 overlays it until expand is done)
+//   k_right u16[R]    bucket slot: right id
+//   k_node  u16[R]    bucket slot: node index (known), NONE16 (BOS), first minimal start (shared unknown slot)
+struct kp_fused_layout {
+    uint32_t nstart, bstart, bcur, binfo, bpos, bcls, t_lc, t_info, t_slot, hy, k_dp, k_right, k_node, total;
+};
+
+static __host__ __device__ inline kp_fused_layout kp_fused_make_layout(uint32_t cap_c, uint32_t cap_k, uint32_t cap_r) {
+    kp_fused_layout L;
+    const uint32_t C1 = cap_c + 2;
+    uint32_t o = 0;
+    L.nstart = o; o += 4 * C1;
+    L.bstart = o; o += 4 * C1;
+    L.bcur = o; o += 4 * C1;
+    L.binfo = o; o += 4 * C1;
+    L.t_lc = o; o += 4 * cap_k;
+    L.t_info = o; o += 4 * cap_k;
+    L.k_dp = o; o += 4 * cap_r;
+    o = (o + 7) & ~7u;
+    L.t_slot = o; o += 2 * cap_k;
+    L.hy = o; o += 2 * (cap_k / 2);
+    L.k_right = o; o += 2 * cap_r;
+    L.k_node = o; o += 2 * cap_r;
+    L.bpos = o; o += 2 * C1;
+    L.bcls = o; o += C1;
+    L.total = (o + 15) & ~15u;
+    return L;
+}
+
+uint32_t kp_fused_smem_bytes(const kp_fused_class& k) { return kp_fused_make_layout(k.cap_c, k.cap_k, k.cap_r).total; }
+
+// ---------------------------------------------------------------------------------------------------------
+// Classification: one thread per sentence.  Sentences go to the list of the first class whose byte limit
+// holds them, the rest (and everything when no class exists) to the pipeline's list.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kp_fused_classify(const uint64_t* __restrict__ off, uint64_t base, uint32_t S,
+                                                         uint32_t B, kp_fused_classes cls, uint32_t* __restrict__ lists,
+                                                         uint32_t* __restrict__ counts, uint32_t* __restrict__ sel,
+                                                         uint32_t* __restrict__ nsel, uint32_t* __restrict__ err,
+                                                         uint32_t* __restrict__ tcount) {
+    const uint32_t s = blockIdx.x * 256 + threadIdx.x;
+    if (s >= S) return;
+    const uint64_t o0 = off[s], o1 = off[s + 1];
+    if (o0 < base || o1 < o0 || o1 - base > B) {
+        atomicOr(&err[1], 1u);
+        tcount[s] = 0;
+        return;
+    }
+    const uint64_t bytes = o1 - o0;
+    for (uint32_t k = 0; k < cls.n; k++)
+        if (bytes <= cls.c[k].max_bytes) {
+            lists[(size_t)k * S + atomicAdd(&counts[k], 1u)] = s;
+            return;
+        }
+    sel[atomicAdd(nsel, 1u)] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The fused kernel: persistent one-warp blocks take sentences from their class's list by ticket.
+// ---------------------------------------------------------------------------------------------------------
+struct kp_fused_args {
+    const uint8_t* text;
+    const uint64_t* off;
+    uint64_t base;
+    const uint32_t* list;      // sentences of this class
+    const uint32_t* count;     // how many
+    uint32_t* cursor;          // ticket counter
+    uint32_t cap_c, cap_k, cap_r;
+    kp_token* stage;
+    uint32_t* tcount;
+    int32_t* eos_cost;
+    uint32_t* sel;             // sentences left to the pipeline ...
+    uint32_t* nsel;            // ... and how many
+    uint32_t* err;             // [0] invalid UTF-8
+    unsigned long long* totals;   // [8] chars, [9] nodes (BOS and EOS included), [10] sentences done here
+};
+
+__global__ void __launch_bounds__(32) kp_fused(const kp_fused_args a, const kp_ddict d) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const kp_fused_layout L = kp_fused_make_layout(a.cap_c, a.cap_k, a.cap_r);
+    uint32_t* const nstart = (uint32_t*)(smem + L.nstart);
+    uint32_t* const bstart = (uint32_t*)(smem + L.bstart);
+    uint32_t* const bcur = (uint32_t*)(smem + L.bcur);
+    uint32_t* const binfo = (uint32_t*)(smem + L.binfo);
+    uint16_t* const bpos = (uint16_t*)(smem + L.bpos);
+    uint8_t* const bcls = smem + L.bcls;
+    uint32_t* const t_lc = (uint32_t*)(smem + L.t_lc);
+    uint32_t* const t_info = (uint32_t*)(smem + L.t_info);
+    uint16_t* const t_slot = (uint16_t*)(smem + L.t_slot);
+    uint16_t* const hy = (uint16_t*)(smem + L.hy);
+    int* const k_dp = (int*)(smem + L.k_dp);
+    uint32_t* const hx = (uint32_t*)(smem + L.k_dp);
+    uint16_t* const k_right = (uint16_t*)(smem + L.k_right);
+    uint16_t* const k_node = (uint16_t*)(smem + L.k_node);
+    uint2* const path = (uint2*)(smem + L.t_slot);
+    __shared__ uint32_t sh_hits;
+    const uint32_t lane = lane_id();
+    const uint32_t n_list = *a.count;
+    const uint32_t cap_h = a.cap_k / 2;
+
+    while (true) {
+        uint32_t ticket = 0;
+        if (lane == 0) ticket = atomicAdd(a.cursor, 1u);
+        ticket = __shfl_sync(KP_FULL, ticket, 0);
+        if (ticket >= n_list) return;
+        const uint32_t s = a.list[ticket];
+        const uint32_t lo = (uint32_t)(a.off[s] - a.base), hi = (uint32_t)(a.off[s + 1] - a.base);
+        const uint32_t nbytes = hi - lo;
+        const uint8_t* const text = a.text + lo;
+        bool give_up = false;                       // does not fit: the pipeline takes the sentence
+
+        // ---- decode: UTF-8 validation (the C ABI must check what &str guarantees), char offsets, classes ----
+        uint32_t n = 0;
+        {
+            uint32_t conts = 0, claimed = 0;
+            bool bad = false;
+            for (uint32_t i0 = 0; i0 < nbytes; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const bool inr = i < nbytes;
+                const uint32_t c = inr ? text[i] : 0x80u;
+                const bool st = inr && !is_cont(c);
+                if (inr && !st) conts++;
+                const uint32_t m = __ballot_sync(KP_FULL, st);
+                if (st) {
+                    const uint32_t len = lead_len(c);
+                    if (len == 0 || i + len > nbytes) {
+                        bad = true;
+                    } else {
+                        uint32_t cp = c;
+                        if (len > 1) {
+                            claimed += len - 1;
+                            const uint32_t c1 = text[i + 1];
+                            uint32_t lo1 = 0x80u, hi1 = 0xBFu;
+                            if (c == 0xE0u) lo1 = 0xA0u;
+                            if (c == 0xEDu) hi1 = 0x9Fu;
+                            if (c == 0xF0u) lo1 = 0x90u;
+                            if (c == 0xF4u) hi1 = 0x8Fu;
+                            if (c1 < lo1 || c1 > hi1) bad = true;
+                            if (len == 2) cp = ((c & 0x1Fu) << 6) | (c1 & 0x3Fu);
+                            else {
+                                const uint32_t c2 = text[i + 2];
+                                if (!is_cont(c2)) bad = true;
+                                if (len == 3) cp = ((c & 0x0Fu) << 12) | ((c1 & 0x3Fu) << 6) | (c2 & 0x3Fu);
+                                else {
+                                    const uint32_t c3 = text[i + 3];
+                                    if (!is_cont(c3)) bad = true;
+                                    cp = ((c & 0x07u) << 18) | ((c1 & 0x3Fu) << 12) | ((c2 & 0x3Fu) << 6) | (c3 & 0x3Fu);
+                                }
+                            }
+                        }
+                        const uint32_t p = n + __popc(m & lanemask_lt());
+                        if (p < a.cap_c) {
+                            // CharCategoryDef::char_category: out-of-table code points use entry 0 (char_category_def.rs:33-38)
+                            bpos[p] = (uint16_t)i;
+                            bcls[p] = d.cat[cp < d.n_cat ? cp : 0];
+                        }
+                    }
+                }
+                n += __popc(m);
+            }
+            if (__reduce_add_sync(KP_FULL, conts) != __reduce_add_sync(KP_FULL, claimed)) bad = true;
+            if (__any_sync(KP_FULL, bad)) {
+                if (lane == 0) {
+                    atomicOr(&a.err[0], 1u);
+                    a.tcount[s] = 0;
+                }
+                continue;
+            }
+            if (n > a.cap_c) give_up = true;
+        }
+        if (!give_up) {
+            if (lane == 0) {
+                bpos[n] = (uint16_t)nbytes;
+                sh_hits = 0;
+            }
+            for (uint32_t q = lane; q <= n + 1; q += 32) {
+                nstart[q] = 0;
+                bcur[q] = 0;
+            }
+            __syncwarp();
+            // unknown-word extent of every start: to the end of its same-class run when the class groups,
+            // at most 1024 chars, else one char (lattice.rs:55-84); the class's unknown ids ride along
+            uint32_t carry = n;
+            for (int32_t k = (int32_t)((n + 31) / 32) - 1; k >= 0; k--) {
+                const uint32_t p = (uint32_t)k * 32 + lane;
+                const bool valid = p < n;
+                const uint32_t cat = valid ? bcls[p] : 0xFFFEu;
+                const uint32_t catn = (p + 1 < n) ? bcls[p + 1] : 0xFFFDu;
+                const uint32_t m = __ballot_sync(KP_FULL, valid && cat != catn);
+                const uint32_t mge = m & ~lanemask_lt();
+                const uint32_t runend = mge ? (uint32_t)k * 32 + (uint32_t)__ffs(mge) : carry;
+                carry = __shfl_sync(KP_FULL, runend, 0);
+                if (valid) {
+                    const kp_catinfo ci = d.catinfo[cat];
+                    const uint32_t uend = (ci.flags & 2u) ? min(runend, p + KP_MAX_UNKNOWN_LEN) : p + 1;
+                    binfo[p] = uend | (ci.unk_count << 11) | ((uint32_t)ci.unk_first << 16);
+                }
+            }
+            if (lane == 0) {
+                binfo[n] = 0;
+                nstart[n] = 1;                      // the EOS node starts at boundary n (lattice.rs:165-175)
+            }
+            __syncwarp();
+
+            // ---- walk: lane = start position (da.rs:155-182; the production walk of kp_lattice_count) ----
+            for (uint32_t p0 = 0; p0 < n; p0 += 32) {
+                const uint32_t p = p0 + lane;
+                if (p < n) {
+                    uint32_t nh = 0;
+                    if (d.da_len > KP_ROOT_ID) {
+                        uint32_t i = bpos[p];
+                        const uint32_t c = text[i];
+                        int prev = KP_ROOT_ID, q = 0;
+                        int2 nq = make_int2(0, 0);
+                        bool alive = false;
+                        int2 f = make_int2(KP_FIRST_SLOW, 0);
+                        if (c < 0xF0u) {
+                            uint32_t cp = c, len = 1;
+                            if (c >= 0xE0u) { cp = ((c & 0x0Fu) << 12) | ((text[i + 1] & 0x3Fu) << 6) | (text[i + 2] & 0x3Fu); len = 3; }
+                            else if (c >= 0x80u) { cp = ((c & 0x1Fu) << 6) | (text[i + 1] & 0x3Fu); len = 2; }
+                            f = d.first[cp];
+                            if (f.x != KP_FIRST_SLOW) {          // arrive in state f.x as if by the character's last byte
+                                i += len - 1;
+                                q = f.x;
+                                alive = f.x >= 0;
+                                nq = make_int2(f.y, 0);
+                                prev = 0;
+                            }
+                        }
+                        if (f.x == KP_FIRST_SLOW) {
+                            q = d.da[KP_ROOT_ID].x + (int)c;                                 // da.rs:160
+                            alive = (uint32_t)q < d.da_len;                                  // Vec::get -> None (da.rs:161)
+                            if (alive) nq = d.da[q];
+                        }
+                        uint32_t nch = 1;            // chars among the bytes consumed, the one being tried included
+                        int c1 = i + 1 < nbytes ? (int)(int8_t)text[i + 1] : 0;
+                        while (alive && nq.y == prev) {                                      // da.rs:162-164
+                            const int ahead = nq.x;                                          // + TERMINATOR (0), da.rs:165
+                            const int q2 = nq.x + (c1 & 0xFF);
+                            const uint32_t i2 = i + 1;
+                            const bool pa = (uint32_t)ahead < d.da_len && (c1 >= -64 || d.mid_char_keys);
+                            const bool p2 = i2 < nbytes && (uint32_t)q2 < d.da_len;
+                            int2 na = make_int2(0, 0), nq2 = make_int2(0, 0);
+                            if (pa) na = d.da[ahead];
+                            if (p2) nq2 = d.da[q2];
+                            int c2 = 0;
+                            if (i2 + 1 < nbytes) c2 = (int)(int8_t)text[i2 + 1];
+                            if (pa && na.y == q && na.x < 0) {                               // da.rs:167-174
+                                const uint32_t id = (uint32_t)(-na.x);
+                                const uint32_t h = atomicAdd(&sh_hits, 1u);
+                                if (h < cap_h && nch <= MAX_NCH) {
+                                    hx[h] = id;
+                                    hy[h] = (uint16_t)(p | (nch << 10));
+                                } else {
+                                    atomicOr(&sh_hits, 0x80000000u);                         // does not fit
+                                }
+                                nh++;
+                            }
+                            nch += c1 >= -64;            // the byte tried next starts a character
+                            prev = q;
+                            q = q2;
+                            nq = nq2;
+                            alive = p2;
+                            c1 = c2;
+                            i = i2;
+                        }
+                    }
+                    // unknown words (lattice.rs:42-99): when nothing matched, or the class always invokes them
+                    const kp_catinfo ci = d.catinfo[bcls[p]];
+                    if ((nh == 0 || (ci.flags & 1u)) && ci.unk_count) {
+                        const uint32_t bi = binfo[p];
+                        binfo[p] = bi | (1u << 10);
+                        atomicOr(&bcur[bi & 1023u], 0x80000000u);
+                    }
+                }
+            }
+            __syncwarp();
+            const uint32_t H = sh_hits;
+            if (H & 0x80000000u) give_up = true;
+
+            // ---- count: duplicates per hit (index.rs:46-51), known nodes per start and per end ----
+            if (!give_up) {
+                bool over = false;
+                for (uint32_t h = lane; h < H; h += 32) {
+                    const uint32_t id = hx[h], y = hy[h];
+                    const uint32_t k = (uint32_t)d.dup[id] + 1;
+                    if (k > MAX_K) over = true;
+                    atomicAdd(&nstart[y & 1023u], k);
+                    atomicAdd(&bcur[(y & 1023u) + (y >> 10)], k);
+                    hx[h] = id | (k << ID_BITS);
+                }
+                if (__any_sync(KP_FULL, over)) give_up = true;
+            }
+        }
+        __syncwarp();
+        uint32_t n_known = 0, n_slots = 0;
+        if (!give_up) {
+            // exclusive scans over the boundaries 0..n: first node of every start, first slot of every bucket
+            uint32_t ca = 0, cb = 0;
+            for (uint32_t q0 = 0; q0 <= n; q0 += 32) {
+                const uint32_t q = q0 + lane;
+                uint32_t va = 0, vb = 0;
+                if (q <= n) {
+                    va = nstart[q];
+                    const uint32_t bc = bcur[q];
+                    vb = (bc & 0x7FFFFFFFu) + (q == 0 ? 1u : 0u);                 // + BOS in edges[0] (lattice.rs:156-164)
+                    if (bc >> 31) vb += (binfo[q - 1] >> 11) & 31u;               // shared slots: the ids of the class before q
+                }
+                uint32_t xa = va, xb = vb;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t ya = __shfl_up_sync(KP_FULL, xa, o), yb = __shfl_up_sync(KP_FULL, xb, o);
+                    if (lane >= (uint32_t)o) {
+                        xa += ya;
+                        xb += yb;
+                    }
+                }
+                if (q <= n) {
+                    nstart[q] = ca + xa - va;
+                    bstart[q] = cb + xb - vb;
+                    bcur[q] = cb + xb - vb + (q == 0 ? 1u : 0u);                  // fill cursor (BOS holds slot 0)
+                }
+                ca += __shfl_sync(KP_FULL, xa, 31);
+                cb += __shfl_sync(KP_FULL, xb, 31);
+            }
+            n_known = ca;
+            n_slots = cb;
+            if (n_known > a.cap_k || n_slots > a.cap_r) give_up = true;
+        }
+        if (give_up) {
+            if (lane == 0) a.sel[atomicAdd(a.nsel, 1u)] = s;
+            continue;
+        }
+        if (lane == 0) bstart[n + 1] = n_slots;
+        __syncwarp();
+
+        // ---- expand: one lane per hit; a known node {left, cost, id} at its start, {right, node} at its end ----
+        if (lane == 0) {
+            const uint32_t i = nstart[n];
+            nstart[n] = i + 1;
+            t_lc[i] = 0;                            // EOS: morph (0,0,0)
+            t_info[i] = EOS_INFO;
+            t_slot[i] = (uint16_t)NONE16;           // ends nowhere
+        }
+        const uint32_t H = sh_hits;
+        for (uint32_t h = lane; h < H; h += 32) {
+            const uint32_t x = hx[h], y = hy[h];
+            const uint32_t id = x & ID_MASK20, k = x >> ID_BITS, p = y & 1023u, nch = y >> 10;
+            const uint32_t i0 = atomicAdd(&nstart[p], k);
+            const uint32_t s0 = atomicAdd(&bcur[p + nch], k);
+            for (uint32_t dd = 0; dd < k; dd++) {                                 // lattice.rs:177-188
+                const uint2 m = ld_morph(d.morphs, id + dd - 1);
+                t_lc[i0 + dd] = (m.x & 0xFFFFu) | (m.y << 16);
+                t_info[i0 + dd] = (id + dd) | (nch << ID_BITS);
+                t_slot[i0 + dd] = (uint16_t)(s0 + dd);
+                k_right[s0 + dd] = (uint16_t)(m.x >> 16);
+                k_node[s0 + dd] = (uint16_t)(i0 + dd);
+            }
+        }
+        __syncwarp();                               // the hits are dead from here on: k_dp takes their place
+        // shared slots of the unknown ids: [bcur[e], bstart[e + 1]); BOS: dp None -> unwrap_or(0) (lattice.rs:127)
+        for (uint32_t e = lane; e <= n; e += 32) {
+            const uint32_t q0 = bcur[e], q1 = bstart[e + 1];
+            if (q1 > q0) {
+                const uint32_t first = binfo[e - 1] >> 16;
+                for (uint32_t q = q0; q < q1; q++) {
+                    k_right[q] = (uint16_t)(ld_morph(d.unk_morphs, first + (q - q0) - 1).x >> 16);
+                    k_dp[q] = INT_MAX;
+                    k_node[q] = 0;
+                }
+            }
+            if (e == 0) {
+                k_dp[0] = 0;
+                k_right[0] = 0;
+                k_node[0] = (uint16_t)NONE16;
+            }
+        }
+        __syncwarp();
+
+        // ---- sweep (lattice.rs:116-143): per boundary, lanes = (target, slice of the predecessors) ----
+        int eos_dp = KP_INF;
+        uint32_t n_unknown = 0;
+        for (uint32_t p = 0; p <= n; p++) {
+            const uint32_t t0 = p ? nstart[p - 1] : 0u, Tk = nstart[p] - t0;
+            const uint32_t bi = binfo[p];
+            const uint32_t Tu = (bi >> 10) & 1u ? (bi >> 11) & 31u : 0u;
+            const uint32_t T = Tk + Tu;
+            n_unknown += Tu;
+            if (T == 0) continue;
+            const uint32_t r0 = bstart[p], R = bstart[p + 1] - r0;
+            uint32_t sh = T <= 1 ? 0u : 32u - (uint32_t)__clz(T - 1);
+            if (sh > 5) sh = 5;
+            const uint32_t W = 1u << sh, J = 32u >> sh;          // targets per pass, predecessor slices
+            const uint32_t il = lane & (W - 1), jo = lane >> sh;
+            const uint32_t ufirst = bi >> 16, ushared = bcur[bi & 1023u];
+            for (uint32_t tc = 0; tc < T; tc += W) {
+                const uint32_t ti = tc + il;
+                const bool tv = ti < T;
+                uint32_t lc = 0;
+                if (tv) {
+                    if (ti < Tk) lc = t_lc[t0 + ti];
+                    else {
+                        const uint2 m = ld_morph(d.unk_morphs, ufirst + (ti - Tk) - 1);   // lattice.rs:195
+                        lc = (m.x & 0xFFFFu) | (m.y << 16);
+                    }
+                }
+                const uint32_t left = lc & 0xFFFFu;
+                int best = INT_MAX;
+                if (tv)
+                    for (uint32_t j = jo; j < R; j += J) {
+                        const int dpj = k_dp[r0 + j];
+                        const int cell = ld_cell(d.connT, k_right[r0 + j], d.connT_stride, left);   // connection.rs:12-14
+                        best = __viaddmin_s32(dpj, cell, best);
+                    }
+                for (uint32_t o = 16; o >= W; o >>= 1) best = min(best, __shfl_xor_sync(KP_FULL, best, o));
+                if (tv && jo == 0) {
+                    int dp = KP_INF;
+                    if (R) dp = min(best + (int)(int16_t)(lc >> 16), KP_INF);            // lattice.rs:127-139
+                    if (ti < Tk) {
+                        const uint32_t slot = t_slot[t0 + ti];
+                        if (slot == NONE16) eos_dp = dp;
+                        else k_dp[slot] = dp;
+                    } else {
+                        const uint32_t q = ushared + (ti - Tk);
+                        if (dp < k_dp[q]) {           // strict: the first minimal start is kept
+                            k_dp[q] = dp;
+                            k_node[q] = (uint16_t)p;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        eos_dp = __shfl_sync(KP_FULL, eos_dp, 0);     // EOS is the only target of boundary n: lane 0 held it
+
+        // ---- back-trace (lattice.rs:144-153): the first predecessor attaining dp, by (start, kind, id) ----
+        uint32_t cnt = 0;
+        {
+            uint32_t cur_id = 0, cur_kind = KP_CLASS_DUMMY, cur_p = n, cur_len = 3, left = 0;
+            int cost = 0, dpc = eos_dp;
+            while (true) {
+                if (dpc >= KP_INF) break;            // pre_nodes[pos] is None
+                const int want = dpc - cost;
+                const uint32_t r0 = bstart[cur_p], r1 = bstart[cur_p + 1], rs = bcur[cur_p];
+                const uint32_t sfirst = cur_p ? binfo[cur_p - 1] >> 16 : 0u;
+                uint32_t best_key = 0xFFFFFFFFu, best_j = 0;
+                for (uint32_t j0 = r0; j0 < r1; j0 += 32) {
+                    const uint32_t j = j0 + lane;
+                    uint32_t key = 0xFFFFFFFFu;
+                    if (j < r1) {
+                        const int dpj = k_dp[j];
+                        if (dpj != INT_MAX && dpj + ld_cell(d.connT, k_right[j], d.connT_stride, left) == want) {
+                            const uint32_t nd = k_node[j];
+                            if (j >= rs) key = (nd << 22) | ((uint32_t)KP_CLASS_UNKNOWN << ID_BITS) | (sfirst + (j - rs));
+                            else if (nd == NONE16) key = 0;                       // BOS
+                            else {
+                                const uint32_t inf = t_info[nd];
+                                key = ((cur_p - (inf >> ID_BITS)) << 22) | ((uint32_t)KP_CLASS_KNOWN << ID_BITS) | (inf & ID_MASK20);
+                            }
+                        }
+                    }
+                    const uint32_t kmin = __reduce_min_sync(KP_FULL, key);
+                    if (kmin < best_key) {
+                        best_key = kmin;
+                        const uint32_t src = (uint32_t)__ffs(__ballot_sync(KP_FULL, key == kmin)) - 1;
+                        best_j = __shfl_sync(KP_FULL, j, src);
+                    }
+                }
+                if (best_key == 0xFFFFFFFFu) break;  // unreachable for a consistent dp table
+                __syncwarp();
+                if (lane == 0) path[cnt] = make_uint2(cur_id | (cur_kind << 30), cur_p | (cur_len << 16));
+                cnt++;
+                if (best_key == 0) break;            // BOS: no predecessor, not emitted
+                // the chosen node becomes the current one
+                const uint32_t nd = k_node[best_j];
+                dpc = k_dp[best_j];
+                if (best_j >= rs) {
+                    cur_kind = KP_CLASS_UNKNOWN;
+                    cur_id = sfirst + (best_j - rs);
+                    cur_len = cur_p - nd;
+                    cur_p = nd;
+                    const uint2 m = ld_morph(d.unk_morphs, cur_id - 1);
+                    left = m.x & 0xFFFFu;
+                    cost = (int)(int16_t)(m.y & 0xFFFFu);
+                } else {
+                    const uint32_t inf = t_info[nd], lc = t_lc[nd];
+                    cur_kind = KP_CLASS_KNOWN;
+                    cur_id = inf & ID_MASK20;
+                    cur_len = inf >> ID_BITS;
+                    cur_p -= cur_len;
+                    left = lc & 0xFFFFu;
+                    cost = (int)(int16_t)(lc >> 16);
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- tokens (tokenizer.rs:22-43), front to back, into the sentence's slot of the staging area ----
+        if (lane == 0) {
+            a.tcount[s] = cnt;
+            a.eos_cost[s] = eos_dp;
+            atomicAdd(&a.totals[8], (unsigned long long)n);
+            atomicAdd(&a.totals[9], (unsigned long long)n_known + n_unknown + 1);   // + BOS
+            atomicAdd(&a.totals[10], 1ull);
+        }
+        uint4* const out = (uint4*)(a.stage + ((size_t)lo + s));
+        for (uint32_t k = lane; k < cnt; k += 32) {
+            const uint2 e = path[cnt - 1 - k];
+            const uint32_t kind = e.x >> 30, p = e.y & 0xFFFFu;
+            // {id, position, start, char_len | cls << 16}; EOS: char_len = "EOS".chars().count()
+            out[k] = make_uint4(e.x & KP_ID_MASK, bpos[p], p, (e.y >> 16) | (kind << 16));
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+bool kp_fused_dict_ok(const kp_ddict& d, const kp_catinfo* host_catinfo) {
+    if (d.n_morphs >= (1u << ID_BITS) || d.n_unk_morphs >= 65536u || d.conn_col > 65536u || d.conn_row > 65536u) return false;
+    for (int c = 0; c < 256; c++)
+        if (host_catinfo[c].unk_count > 31u || (uint32_t)host_catinfo[c].unk_first + host_catinfo[c].unk_count > 65535u)
+            return false;
+    return true;
+}
+
+static int kp_fused_check(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        kp_set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+        return KP_ERR_CUDA;
+    }
+    return 1;
+}
+
+int kp_fused_prepare(kp_fused_classes* cls, int device) {
+    // opt in to large dynamic shared memory once, and learn how many one-warp blocks of each class fit an SM
+    int sms = 0, max_optin = 0;
+    KP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    KP_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    uint32_t largest = 0;
+    for (uint32_t k = 0; k < cls->n; k++) {
+        cls->c[k].smem = kp_fused_smem_bytes(cls->c[k]);
+        largest = cls->c[k].smem > largest ? cls->c[k].smem : largest;
+    }
+    if ((int)largest > max_optin) {
+        kp_set_error("fused kernel class needs %u bytes of shared memory, the device offers %d", largest, max_optin);
+        return KP_ERR_ARG;
+    }
+    KP_CUDA(cudaFuncSetAttribute(kp_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)largest));
+    KP_CUDA(cudaFuncSetAttribute(kp_fused, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    for (uint32_t k = 0; k < cls->n; k++) {
+        int per_sm = 0;
+        KP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kp_fused, 32, cls->c[k].smem));
+        if (per_sm < 1) per_sm = 1;
+        cls->c[k].blocks = (uint32_t)(per_sm * sms);
+    }
+    return KP_OK;
+}
+
+int kp_launch_fused_classify(const kp_chunk& c, const kp_fused_classes& cls, uint32_t* lists, uint32_t* counts,
+                             uint32_t* nsel, cudaStream_t st) {
+    if (c.S_all == 0) return 0;
+    kp_fused_classify<<<(c.S_all + 255) / 256, 256, 0, st>>>(c.off, c.base, c.S_all, c.B, cls, lists, counts, (uint32_t*)c.sel_out,
+                                                              nsel, c.err, c.tcount);
+    return kp_fused_check("kp_fused_classify");
+}
+
+int kp_launch_fused(const kp_chunk& c, const kp_ddict& d, const kp_fused_class& k, const uint32_t* list,
+                    const uint32_t* count, uint32_t* cursor, uint32_t* nsel, uint32_t expected, cudaStream_t st) {
+    kp_fused_args a;
+    a.text = c.text;
+    a.off = c.off;
+    a.base = c.base;
+    a.list = list;
+    a.count = count;
+    a.cursor = cursor;
+    a.cap_c = k.cap_c;
+    a.cap_k = k.cap_k;
+    a.cap_r = k.cap_r;
+    a.stage = c.stage;
+    a.tcount = c.tcount;
+    a.eos_cost = c.eos_cost;
+    a.sel = (uint32_t*)c.sel_out;
+    a.nsel = nsel;
+    a.err = c.err;
+    a.totals = (unsigned long long*)c.totals;
+    uint32_t blocks = k.blocks;
+    if (expected < blocks) blocks = expected ? expected : 1;
+    kp_fused<<<blocks, 32, k.smem, st>>>(a, d);
+    return kp_fused_check("kp_fused");
+}

@@ -43,6 +43,7 @@ struct kp_chunk {
     uint32_t S_all;          // sentences of the chunk
     const uint32_t* sel;     // [S] chunk sentence behind each slot of this pass (nullptr = identity); outputs
                              // (eos_cost, tcount, staged tokens) are indexed by chunk sentence
+    uint32_t* sel_out;       // [S_all] list the fused path appends the sentences it leaves to the pipeline to
     // sizes learnt on the way
     uint32_t C, NB, N;
     // scratch (device)
@@ -93,3 +94,24 @@ int kp_launch_scan2(const uint32_t* in_a, const uint32_t* in_b, uint32_t* out_a,
                     uint64_t* tmp, uint64_t* total_a, uint64_t* total_b, cudaStream_t st);
 int kp_launch_common_prefix(const kp_ddict& d, const uint8_t* d_text, uint32_t len, int expand_dup, int64_t* d_ids,
                             uint64_t* d_lens, uint32_t cap, uint32_t* d_n, cudaStream_t st);
+
+// ---- fused per-sentence path (kp_fused.cu) --------------------------------------------------------------
+// A class = the sentences of at most max_bytes bytes, run by one-warp blocks with room for cap_c chars,
+// cap_k known nodes (EOS included; cap_k / 2 trie hits) and cap_r reduced bucket slots in shared memory.
+constexpr uint32_t KP_FUSED_MAX_CLASSES = 6;
+struct kp_fused_class {
+    uint32_t max_bytes, cap_c, cap_k, cap_r;
+    uint32_t smem, blocks;   // filled by kp_fused_prepare: dynamic shared memory per block, persistent blocks to launch
+};
+struct kp_fused_classes {
+    uint32_t n;
+    kp_fused_class c[KP_FUSED_MAX_CLASSES];
+};
+uint32_t kp_fused_smem_bytes(const kp_fused_class& k);
+bool kp_fused_dict_ok(const kp_ddict& d, const kp_catinfo* host_catinfo);
+int kp_fused_prepare(kp_fused_classes* cls, int device);
+// lists: [cls.n][S_all] sentence lists per class; counts: [cls.n]; nsel: sentences left to the pipeline (c.sel_out)
+int kp_launch_fused_classify(const kp_chunk& c, const kp_fused_classes& cls, uint32_t* lists, uint32_t* counts,
+                             uint32_t* nsel, cudaStream_t st);
+int kp_launch_fused(const kp_chunk& c, const kp_ddict& d, const kp_fused_class& k, const uint32_t* list,
+                    const uint32_t* count, uint32_t* cursor, uint32_t* nsel, uint32_t expected, cudaStream_t st);

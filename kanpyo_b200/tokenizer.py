@@ -305,6 +305,9 @@ class Queue:
         _lib.check(self._L.kp_queue_create(dict.device_handle(device), depth, C.byref(self._h)))
         self._keep = {}
 
+    def set_path(self, path: str):
+        _lib.check(self._L.kp_queue_set_path(self._h, {"auto": 0, "pipeline": 1, "fused": 2}[path]))
+
     def submit_ptr(self, text_ptr: int, offsets_ptr: int, n_sent: int) -> int:
         tk = C.c_uint64()
         _lib.check(self._L.kp_queue_submit(self._h, text_ptr, offsets_ptr, n_sent, C.byref(tk)))

@@ -507,3 +507,50 @@ def test_graphviz_matches_oracle(gpu_tok, oracle_tok):
     for s in ["すもももももももものうち", "Tシャツを3枚買ったABC", "", "東京都に住んでいます。", "\U0001F600の犬", "カタカナ語"]:
         for full in (False, True):
             assert graphviz(gpu_tok, s, dpi=72, full_state=full) == ograph.graphviz(oracle_tok, s, 72, full), (s, full)
+
+
+# ---- the two device paths: fused per-sentence kernel (default where a sentence fits) and the pipeline -----
+EDGE_SENTENCES = ["", "あ", "すもももももももものうち", "Tシャツを3枚買ったABC", "\U0001F600の犬", "ｶﾀｶﾅとカタカナと12345と hello world",
+                  "東京都に住んでいます。", "ー" * 300, "a" * 500, "犬" * 200, "ア" * 1030, "9" * 1023 + "a", "\x00あ\x00い",
+                  "𠮷野家で𩸽を食べた", "ヴァイオリンとヴィオラ", " ", "。。。", "1" * 60 + "犬" + "ア" * 40 + "abc" * 30]
+
+
+@pytest.mark.parametrize("path", ["fused", "pipeline"])
+def test_both_paths_on_edge_cases(gpu_ipadic, oracle_tok, oracle_mod, path):
+    import kanpyo_b200
+    t = kanpyo_b200.Tokenizer(gpu_ipadic, device=0)
+    t.set_path(path)
+    try:
+        _check_sentences(t, oracle_tok, EDGE_SENTENCES)
+        fused = t.profile()["fused_sentences"]
+        # short sentences run in the fused kernel; the 1030-char run and the 1024-char one exceed every class
+        assert (fused > 10 and fused < len(EDGE_SENTENCES)) if path == "fused" else fused == 0
+        for s in EDGE_SENTENCES:
+            _check_sentences(t, oracle_tok, [s])
+    finally:
+        t.close()
+    # the reference's fixture: no unknown entry for DEFAULT -> dead nodes, cut and empty paths
+    od = reference_fixture_dict(oracle_mod)
+    g = kanpyo_b200.Tokenizer(to_product_dict(od), device=0)
+    g.set_path(path)
+    try:
+        _check_sentences(g, oracle_mod.OracleTokenizer(od),
+                         ["テスト", "", "あいうえお", "辞書テスト形態素", "テスト辞書あい形態素うえ", "xyz", "漢字テスト", "xテスト", "テストx",
+                          "xx", "テxスト", "x"])
+    finally:
+        g.close()
+
+
+def test_fused_path_takes_the_short_sentences(gpu_tok, oracle_tok, vocab):
+    """On the cfg2 / cfg3 corpora nearly every sentence fits a size class of the fused kernel; the rest goes
+    through the pipeline in the same call, and the packed result is the oracle's either way."""
+    from kanpyo_b200 import corpus
+    for kind, n in (("cfg2", 8000), ("cfg3", 8000)):
+        text, off = corpus.synth_corpus(vocab, n, kind, seed=21)
+        res = gpu_tok.tokenize_batch_bytes(text, off)
+        p = gpu_tok.profile()
+        o_off, o_tok, o_cost, ctr = oracle_tok.tokenize_batch(text, off, threads=os.cpu_count() or 8)
+        assert_batch_equal(res, o_off, o_tok, o_cost)
+        c = gpu_tok.counters()
+        assert (c["bytes"], c["chars"], c["nodes"], c["tokens"]) == (ctr["B"], ctr["C"], ctr["N"], ctr["T"])
+        assert p["fused_sentences"] > 0.95 * n, p

@@ -384,12 +384,14 @@ def product_arm(args):
     barrier()
     w0 = time.perf_counter()
     dev_ms, gather_ms_sum, stages, launches = [], 0.0, {}, 0
+    fused_sentences = 0
     g_last = None
     for _ in range(args.steps):
         r, p, g_last, gms = step_device()
         dev_ms.append(p["total_ms"] + gms)
         gather_ms_sum += gms
         launches += p["kernel_launches"]
+        fused_sentences = p.get("fused_sentences", 0)
         for k in ("prep_ms", "lattice_ms", "bucket_ms", "viterbi_ms", "backtrace_ms", "fused_ms"):
             stages[k] = stages.get(k, 0.0) + p.get(k, 0.0)
     barrier()
@@ -602,6 +604,7 @@ def product_arm(args):
                                         "kernel_ms": kern_ms, "achieved": a_total / (kern_ms * 1e-3) / 1e9,
                                         "frac": a_total / (kern_ms * 1e-3) / 1e9 / peak}},
             "stages_ms_per_step": {k: v / K for k, v in stages.items()},
+            "fused_sentences_per_step": fused_sentences,
             "counters": ctr,
             "clocks": clocks,
         }

@@ -202,10 +202,15 @@ int kp_copy_to_host(kp_tokenizer* t, void* dst, const void* device_src, uint64_t
 /* Blocks until all work queued by this tokenizer is complete. */
 int kp_tokenizer_sync(kp_tokenizer* t);
 
-/* Which device path kp_tokenize* takes: KP_PATH_AUTO (default) runs the fused per-sentence kernel for
- * sentences that fit its shared-memory budget and the multi-kernel pipeline for the rest;
- * KP_PATH_PIPELINE forces the pipeline, KP_PATH_FUSED = AUTO (the pipeline still takes what does not
- * fit).  Results are identical; the switch exists for measurements and parity tests. */
+/* Which device path kp_tokenize* takes.  Two exist, with identical results (tests run both):
+ *   the pipeline  a dozen kernels over the whole batch with the lattice in HBM: the throughput path, it needs
+ *                 tens of thousands of sentences in flight to hide its dependent gathers;
+ *   the fused kernel  one warp owns one sentence from its bytes to its tokens in shared memory: one launch and,
+ *                 for batches of at most 64 sentences / 48 KiB, ONE host round trip per call -- the path for
+ *                 the reference's own call pattern (one line per call) and for small batches.
+ * KP_PATH_AUTO (default) picks by batch size (fused up to 2048 sentences per chunk); sentences that do not fit
+ * the fused kernel's shared-memory budget go through the pipeline in the same call.  KP_PATH_PIPELINE and
+ * KP_PATH_FUSED force one path for every batch size (measurements, parity tests). */
 enum { KP_PATH_AUTO = 0, KP_PATH_PIPELINE = 1, KP_PATH_FUSED = 2 };
 int kp_tokenizer_set_path(kp_tokenizer* t, int path);
 

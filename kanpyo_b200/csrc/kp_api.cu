@@ -74,6 +74,9 @@ struct PinBuf {   // pinned host memory, preserved on growth
 };
 
 constexpr uint32_t KP_PERM_REFRESH = 16;
+#ifndef KP_FUSED_AUTO_SENTENCES
+#define KP_FUSED_AUTO_SENTENCES 4096   // KP_PATH_AUTO: batches up to this many sentences take the fused kernel
+#endif
 #ifndef KP_FUSED_BYTES
 #define KP_FUSED_BYTES 192, 256, 320, 448, 768, 1536     // byte limits of the fused kernel's size classes
 #endif
@@ -94,6 +97,10 @@ struct kp_tokenizer {
     cudaStream_t fstream[KP_FUSED_MAX_CLASSES] = {};
     cudaEvent_t fev_fork = nullptr, fev_join[KP_FUSED_MAX_CLASSES] = {};
     DevBuf flists, fctl;
+    DevBuf small_in, small_out;        // small-batch path: one staging block in, one block out
+    PinBuf h_small_in, h_small_out;
+    uint64_t small_calls = 0;
+    uint32_t fused_max_batch = KP_FUSED_AUTO_SENTENCES;
     kp_perm perm = {};
     uint32_t perm_age = 0;     // passes since the column order was last ranked
     DevBuf perm_hist, perm_map, perm_conn;
@@ -110,6 +117,9 @@ struct kp_tokenizer {
     bool pipeline_timed = false;
     uint64_t last_tokens = 0;
     kp_chunk pass = {};        // chunk of a two-phase pass (kp_pass_begin / kp_pass_pack)
+    const void* res_tok_off = nullptr;   // host result of the last kp_tokenize_batch[8] call
+    const void* res_tokens = nullptr;
+    const int32_t* res_eos = nullptr;
 };
 
 namespace {
@@ -260,14 +270,20 @@ int run_fused(kp_tokenizer* t, kp_chunk& c, uint32_t* left) {
     KP_CUDA(cudaEventRecord(t->ev[EV_FUSED0], st));
     KP_LAUNCH(kp_launch_fused_classify(c, t->fclasses, t->flists.as<uint32_t>(), fctl, fctl + 16, st));
     KP_CUDA(cudaEventRecord(t->fev_fork, st));
-    for (uint32_t i = 0; i < nc; i++) {
-        const uint32_t k = nc - 1 - i;               // largest sentences first
+    // classes 0 .. nc-2 side by side (larger first: the tail of one overlaps the start of the next); a sentence that
+    // overflows its class is appended to the LAST class's list, whose kernel runs after the others; only what
+    // overflows that one is left to the pipeline
+    uint32_t* const esc_list = t->flists.as<uint32_t>() + (size_t)(nc - 1) * S;
+    for (uint32_t i = 1; i < nc; i++) {
+        const uint32_t k = nc - 1 - i;
         KP_CUDA(cudaStreamWaitEvent(t->fstream[k], t->fev_fork, 0));
         KP_LAUNCH(kp_launch_fused(c, d, t->fclasses.c[k], t->flists.as<uint32_t>() + (size_t)k * S, fctl + k, fctl + 8 + k,
-                                  fctl + 16, S, t->fstream[k]));
+                                  esc_list, fctl + (nc - 1), S, t->fstream[k]));
         KP_CUDA(cudaEventRecord(t->fev_join[k], t->fstream[k]));
         KP_CUDA(cudaStreamWaitEvent(st, t->fev_join[k], 0));
     }
+    KP_LAUNCH(kp_launch_fused(c, d, t->fclasses.c[nc - 1], esc_list, fctl + (nc - 1), fctl + 8 + (nc - 1), c.sel_out, fctl + 16,
+                              S, st));
     KP_CUDA(cudaEventRecord(t->ev[EV_FUSED1], st));
     KP_CUDA(cudaMemcpyAsync(h_err, c.err, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaMemcpyAsync(h_ctl, fctl, sizeof(uint32_t) * 32, cudaMemcpyDeviceToHost, st));
@@ -318,7 +334,12 @@ int chunk_compute(kp_tokenizer* t, kp_chunk& c, uint64_t* n_tokens, StageTimes* 
     KP_CUDA(cudaMemsetAsync(c.totals, 0, sizeof(uint64_t) * 16, st));
     KP_CUDA(cudaMemsetAsync(c.err, 0, sizeof(uint32_t) * 4, st));
     t->pipeline_timed = false;
-    if (t->fused_ok && t->path_mode != KP_PATH_PIPELINE && !t->count_work && S > 0) {
+    // which device path: the fused per-sentence kernel keeps a sentence on chip but holds few sentences per SM, so
+    // it wins where the batch is too small to fill the pipeline's kernels (and for single sentences, where the
+    // pipeline's dozen launches and three round trips dominate); KP_PATH_FUSED / _PIPELINE force either one
+    const bool fused = t->fused_ok && !t->count_work && S > 0 &&
+                       (t->path_mode == KP_PATH_FUSED || (t->path_mode == KP_PATH_AUTO && S <= t->fused_max_batch));
+    if (fused) {
         // fused per-sentence kernel first; the pipeline then takes the sentences it left (c.sel)
         uint32_t left = 0;
         KP_TRY(run_fused(t, c, &left));
@@ -449,10 +470,10 @@ extern "C" void kp_tokenizer_destroy(kp_tokenizer* t) {
     if (t->stream) cudaStreamSynchronize(t->stream);
     DevBuf* bufs[] = {&t->text, &t->off, &t->nchar, &t->coff, &t->binfo, &t->ncount, &t->noff, &t->bcount, &t->boff,
                       &t->bfill, &t->ucount, &t->rbk, &t->nhit, &t->hits, &t->rec, &t->tgt, &t->red, &t->ndp, &t->bnode, &t->path, &t->pre, &t->lenhist, &t->order, &t->tcount, &t->toff32,
-                      &t->scan_tmp, &t->totals, &t->err, &t->stage, &t->sel, &t->flists, &t->fctl, &t->d_tok_off, &t->d_tokens, &t->d_eos, &t->perm_hist, &t->perm_map,
+                      &t->scan_tmp, &t->totals, &t->err, &t->stage, &t->sel, &t->flists, &t->fctl, &t->small_in, &t->small_out, &t->d_tok_off, &t->d_tokens, &t->d_eos, &t->perm_hist, &t->perm_map,
                       &t->perm_conn};
     for (DevBuf* b : bufs) b->release();
-    PinBuf* pins[] = {&t->h_totals, &t->h_tok_off, &t->h_tokens, &t->h_eos, &t->h_misc};
+    PinBuf* pins[] = {&t->h_totals, &t->h_tok_off, &t->h_tokens, &t->h_eos, &t->h_misc, &t->h_small_in, &t->h_small_out};
     for (PinBuf* b : pins) b->release();
     for (int i = 0; i < EV_COUNT; i++)
         if (t->ev[i]) cudaEventDestroy(t->ev[i]);
@@ -573,11 +594,132 @@ extern "C" int kp_tokenize_batch_device8(kp_tokenizer* t, const uint8_t* d_utf8,
     return KP_OK;
 }
 
+// ---- small batches (the reference's own call pattern is one line per call, src/bin/kanpyo.rs:115-122) ----
+// Up to KP_SMALL_SENT sentences / KP_SMALL_BYTES bytes go through the fused kernel with ONE host round trip:
+// the host sorts the sentences into the size classes (it knows their byte lengths), one staging block goes
+// in (offsets, class lists, counters), the class kernels + scan + pack run back to back, and one block comes
+// out (counters, flags, token offsets, dp[EOS], and the token records up to their upper bound bytes +
+// sentences).  Returns 1 when the batch was done here, 0 when the general path has to take it (something
+// did not fit the fused kernel), negative on error.
+constexpr uint64_t KP_SMALL_SENT = 64, KP_SMALL_BYTES = 48 << 10;
+
+static inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+
+int tokenize_small(kp_tokenizer* t, const uint8_t* utf8, const uint64_t* offsets, uint64_t n_sent, bool compact,
+                   uint64_t* n_tokens, const void** h_tok_off, const void** h_tokens, const int32_t** h_eos) {
+    const uint32_t S = (uint32_t)n_sent, nc = t->fclasses.n;
+    const uint64_t nbytes = offsets[n_sent] - offsets[0];
+    cudaStream_t st = t->stream;
+    const kp_ddict& d = t->dict->view;
+    const size_t tok_sz = compact ? sizeof(kp_token8) : sizeof(kp_token), off_sz = compact ? sizeof(uint32_t) : sizeof(uint64_t);
+    const size_t bound = nbytes + S;                        // tokens <= chars + sentences <= bytes + sentences
+    // staging in: [totals u64 x16 | err u32 x4 | fctl u32 x32 | offsets u64 x(S+1) | lists u32 x nc*S]
+    const size_t in_tot = 0, in_err = 128, in_ctl = 144, in_off = 272, in_lists = in_off + 8 * (size_t)(S + 1);
+    const size_t in_bytes = align16(in_lists + 4 * (size_t)nc * S);
+    // block out: [totals | err | fctl | tok_off | eos | tokens]
+    const size_t out_off = 272, out_eos = align16(out_off + off_sz * (S + 1)), out_tok = align16(out_eos + 4 * (size_t)S);
+    const size_t out_bytes = out_tok + tok_sz * bound;
+    KP_TRY(t->small_in.ensure(in_bytes));
+    KP_TRY(t->small_out.ensure(out_bytes));
+    KP_TRY(t->h_small_in.ensure(in_bytes, 0));
+    KP_TRY(t->h_small_out.ensure(out_bytes, 0));
+    KP_TRY(t->text.ensure(nbytes + 16));
+    KP_TRY(t->tcount.ensure(sizeof(uint32_t) * (S + 1)));
+    KP_TRY(t->toff32.ensure(sizeof(uint32_t) * (S + 2)));
+    KP_TRY(t->stage.ensure(sizeof(kp_token) * (bound + 2)));
+    KP_TRY(t->scan_tmp.ensure(sizeof(uint64_t) * kp_scan_tmp_elems(S + 1)));
+    KP_TRY(t->sel.ensure(sizeof(uint32_t) * (S + 1)));
+    char* hin = (char*)t->h_small_in.p;
+    memset(hin, 0, in_off);
+    memcpy(hin + in_off, offsets, 8 * (size_t)(S + 1));
+    uint32_t* h_ctl = (uint32_t*)(hin + in_ctl);
+    uint32_t* h_lists = (uint32_t*)(hin + in_lists);
+    // one launch: every sentence runs in the class the longest one needs (a handful of blocks: occupancy is moot,
+    // serialising several class kernels would not be)
+    uint32_t kmax = 0;
+    for (uint32_t s = 0; s < S; s++) {
+        const uint64_t b = offsets[s + 1] - offsets[s];
+        while (kmax < nc && b > t->fclasses.c[kmax].max_bytes) kmax++;
+        if (kmax == nc) return 0;                           // longer than every class: the general path
+    }
+    for (uint32_t s = 0; s < S; s++) h_lists[(size_t)kmax * S + h_ctl[kmax]++] = s;
+    char* din = (char*)t->small_in.p;
+    char* dout = (char*)t->small_out.p;
+    KP_CUDA(cudaEventRecord(t->ev[EV_START], st));
+    if (nbytes) KP_CUDA(cudaMemcpyAsync(t->text.p, utf8 + offsets[0], nbytes, cudaMemcpyHostToDevice, st));
+    KP_CUDA(cudaMemcpyAsync(din, hin, in_bytes, cudaMemcpyHostToDevice, st));
+    kp_chunk c;
+    memset(&c, 0, sizeof(c));
+    c.text = t->text.as<uint8_t>();
+    c.off = (const uint64_t*)(din + in_off);
+    c.base = offsets[0];
+    c.S = c.S_all = S;
+    c.B = (uint32_t)nbytes;
+    c.totals = (uint64_t*)(din + in_tot);
+    c.err = (uint32_t*)(din + in_err);
+    c.tcount = t->tcount.as<uint32_t>();
+    c.toff32 = t->toff32.as<uint32_t>();
+    c.stage = t->stage.as<kp_token>();
+    c.scan_tmp = t->scan_tmp.as<uint64_t>();
+    c.sel_out = t->sel.as<uint32_t>();
+    c.tok_off = dout + out_off;
+    c.eos_cost = (int32_t*)(dout + out_eos);
+    c.tokens = dout + out_tok;
+    uint32_t* fctl = (uint32_t*)(din + in_ctl);
+    KP_CUDA(cudaEventRecord(t->ev[EV_H2D], st));
+    KP_CUDA(cudaEventRecord(t->ev[EV_FUSED0], st));
+    for (uint32_t i = 0; i < nc; i++) {
+        const uint32_t k = nc - 1 - i;
+        if (h_ctl[k] == 0) continue;
+        KP_LAUNCH(kp_launch_fused(c, d, t->fclasses.c[k], (const uint32_t*)(din + in_lists) + (size_t)k * S, fctl + k, fctl + 8 + k,
+                                  c.sel_out, fctl + 16, h_ctl[k], st));
+    }
+    KP_CUDA(cudaEventRecord(t->ev[EV_FUSED1], st));
+    KP_LAUNCH(kp_launch_scan(c.tcount, c.toff32, S, c.scan_tmp, &c.totals[3], st));
+    KP_LAUNCH(kp_launch_tokens_pack(c, 0, compact, st));
+    KP_CUDA(cudaEventRecord(t->ev[EV_PACK], st));
+    KP_CUDA(cudaMemcpyAsync(dout, din, 272, cudaMemcpyDeviceToDevice, st));          // counters + flags ride out with the result
+    KP_CUDA(cudaMemcpyAsync(t->h_small_out.p, dout, out_bytes, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaEventRecord(t->ev[EV_END], st));
+    KP_CUDA(cudaEventSynchronize(t->ev[EV_END]));
+    const char* hout = (const char*)t->h_small_out.p;
+    const uint64_t* r_tot = (const uint64_t*)hout;
+    const uint32_t* r_err = (const uint32_t*)(hout + in_err);
+    const uint32_t* r_ctl = (const uint32_t*)(hout + in_ctl);
+    if (r_err[1]) {
+        kp_set_error("sentence offsets are not ascending or exceed the text length");
+        return KP_ERR_ARG;
+    }
+    if (r_err[0]) {
+        kp_set_error("input contains invalid UTF-8");
+        return KP_ERR_UTF8;
+    }
+    if (r_ctl[16]) return 0;                                 // a sentence did not fit its class: the general path
+    *n_tokens = r_tot[3];
+    *h_tok_off = hout + out_off;
+    *h_eos = (const int32_t*)(hout + out_eos);
+    *h_tokens = hout + out_tok;
+    t->counters.bytes = nbytes;
+    t->counters.chars = r_tot[8];
+    t->counters.nodes = r_tot[9];
+    t->counters.tokens = r_tot[3];
+    t->counters.sentences = S;
+    t->profile.fused_sentences = (uint32_t)r_tot[10];
+    t->profile.chunks = 1;
+    cudaEventElapsedTime(&t->profile.h2d_ms, t->ev[EV_START], t->ev[EV_H2D]);
+    cudaEventElapsedTime(&t->profile.fused_ms, t->ev[EV_FUSED0], t->ev[EV_FUSED1]);
+    cudaEventElapsedTime(&t->profile.d2h_ms, t->ev[EV_PACK], t->ev[EV_END]);
+    cudaEventElapsedTime(&t->profile.total_ms, t->ev[EV_START], t->ev[EV_END]);
+    t->small_calls++;
+    return 1;
+}
+
 // Host text in, host result out, chunk by chunk.  compact = kp_token8 records + 32-bit offsets.
 // The device result of a chunk is sized by its token COUNT of the previous call when that is known
 // to be enough, so the D2H moves the tokens that exist, not an upper bound.
 static int kp_tokenize_host(kp_tokenizer* t, const uint8_t* utf8, const uint64_t* offsets, uint64_t n_sent, bool compact) {
     if (!t || !offsets) return KP_ERR_ARG;
+    t->res_tok_off = nullptr;
     if (n_sent && offsets[n_sent] > offsets[0] && !utf8) return KP_ERR_ARG;
     for (uint64_t s = 0; s < n_sent; s++)
         if (offsets[s + 1] < offsets[s]) {
@@ -586,6 +728,18 @@ static int kp_tokenize_host(kp_tokenizer* t, const uint8_t* utf8, const uint64_t
         }
     KP_CUDA(cudaSetDevice(t->device));
     begin_call(t);
+    if (n_sent >= 1 && n_sent <= KP_SMALL_SENT && offsets[n_sent] - offsets[0] <= KP_SMALL_BYTES && t->fused_ok &&
+        t->path_mode != KP_PATH_PIPELINE && !t->count_work) {
+        uint64_t ntok = 0;
+        const int rc = tokenize_small(t, utf8, offsets, n_sent, compact, &ntok, &t->res_tok_off, &t->res_tokens, &t->res_eos);
+        if (rc < 0) return rc;
+        if (rc == 1) {
+            t->last_tokens = ntok;
+            return KP_OK;
+        }
+        t->res_tok_off = nullptr;
+        begin_call(t);
+    }
     cudaStream_t st = t->stream;
     const size_t tok_sz = compact ? sizeof(kp_token8) : sizeof(kp_token);
     const size_t off_sz = compact ? sizeof(uint32_t) : sizeof(uint64_t);
@@ -644,6 +798,9 @@ static int kp_tokenize_host(kp_tokenizer* t, const uint8_t* utf8, const uint64_t
     t->profile.d2h_ms = d2h_ms;
     t->profile.total_ms = total_ms;
     t->last_tokens = tok_total;
+    t->res_tok_off = t->h_tok_off.p;
+    t->res_tokens = t->h_tokens.p;
+    t->res_eos = t->h_eos.as<int32_t>();
     return KP_OK;
 }
 
@@ -701,9 +858,9 @@ extern "C" int kp_tokenize_batch(kp_tokenizer* t, const uint8_t* utf8, const uin
     KP_TRY(kp_tokenize_host(t, utf8, offsets, n_sent, false));
     out->n_sent = n_sent;
     out->n_tokens = t->last_tokens;
-    out->tok_off = t->h_tok_off.as<uint64_t>();
-    out->tokens = t->h_tokens.as<kp_token>();
-    out->eos_cost = t->h_eos.as<int32_t>();
+    out->tok_off = (const uint64_t*)t->res_tok_off;
+    out->tokens = (const kp_token*)t->res_tokens;
+    out->eos_cost = t->res_eos;
     return KP_OK;
 }
 
@@ -713,9 +870,9 @@ extern "C" int kp_tokenize_batch8(kp_tokenizer* t, const uint8_t* utf8, const ui
     KP_TRY(kp_tokenize_host(t, utf8, offsets, n_sent, true));
     out->n_sent = n_sent;
     out->n_tokens = t->last_tokens;
-    out->tok_off = t->h_tok_off.as<uint32_t>();
-    out->tokens = t->h_tokens.as<kp_token8>();
-    out->eos_cost = t->h_eos.as<int32_t>();
+    out->tok_off = (const uint32_t*)t->res_tok_off;
+    out->tokens = (const kp_token8*)t->res_tokens;
+    out->eos_cost = t->res_eos;
     return KP_OK;
 }
 

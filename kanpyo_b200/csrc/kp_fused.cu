@@ -62,54 +62,65 @@ __device__ __forceinline__ uint32_t lead_len(uint32_t c) {  // 0 = not a valid l
 __device__ __forceinline__ uint2 ld_morph(const short4* __restrict__ m, uint32_t i) {   // {left | right << 16, cost}
     return __ldg((const uint2*)m + i);
 }
-__device__ __forceinline__ int ld_cell(const int16_t* __restrict__ connT, uint32_t right, uint32_t stride, uint32_t left) {
-    return (int)__ldg(connT + (size_t)right * stride + left);
-}
-
 }  // namespace
 
 // Shared-memory layout of one warp's sentence (byte offsets).  C1 = cap_c + 2 boundary entries.
+//   unk_lc  u32[64]   unknown morphs {left | cost << 16}, unk_ro u32[64] their row offsets right * stride
+//                     (copied once per block; dictionaries with more unknown morphs are not eligible)
 //   nstart  u32[C1]   known nodes starting at p: count -> first index -> (after expand) END index
 //   bstart  u32[C1]   reduced-bucket size of boundary e -> first slot (bstart[n+1] = slots in use)
 //   bcur    u32[C1]   known nodes ending at e (| bit 31: an unknown node ends here) -> fill cursor ->
 //                     (after expand) first SHARED slot of bucket e
-//   binfo   u32[C1]   per start: unknown end (10) | emits unknown << 10 | class unk_count (5) << 11 | unk_first << 16
-//   bpos    u16[C1]   byte offset of char p inside the sentence (bpos[n] = bytes)
-//   bcls    u8 [C1]   class of char p
+//   binfo   u32[C1]   per start: unknown end (10) | emits unknown << 10 | class unk_count (5) << 11 | unk_first (8) << 16
+//                     | class invokes unknown words << 24
+//   udesc   u32[C1]   per start: first shared slot of the bucket its unknown nodes end in | unk_first << 16
+//   desc    uint2[C1] per boundary, what one step of the sweep needs in one load:
+//                     {first target | known targets << 12 | targets << 22, first slot | slots << 12 | lane split << 24}
 //   t_lc    u32[K]    known node: left | cost << 16                      (K = cap_k, index = node)
 //   t_info  u32[K]    known node: id | chars << 20; EOS_INFO for the EOS node
 //   t_slot  u16[K]    known node: its slot in the bucket of its end      } the path {id|kind<<30, start|chars<<16}
 //   hy      u16[K/2]  hit: start (10) | chars (6) << 10                   } overlays these two after the sweep
-//   k_dp    i32[R]    bucket slot: dp (hx u32[K/2]: hit id | k << 20 overlays it until expand is done)
-//   k_right u16[R]    bucket slot: right id
-//   k_node  u16[R]    bucket slot: node index (known), NONE16 (BOS), first minimal start (shared unknown slot)
+//   k_dr    int2[R+1] bucket slot: {dp, row offset of right_id in connT}; slot R is where EOS (which ends nowhere)
+//                     parks its dp.  hx u32[K/2] (hit id | k << 20) overlays it until the hits are expanded
+//   k_node  u16[R+1]  bucket slot: node index (known), NONE16 (BOS), first minimal start (shared unknown slot)
+//   bpos    u16[C1]   byte offset of char p inside the sentence (bpos[n] = bytes)
+//   bcls    u8 [C1]   class of char p
+//   tbytes  u8 [max_bytes + 8]   the sentence's bytes
 struct kp_fused_layout {
-    uint32_t nstart, bstart, bcur, binfo, bpos, bcls, t_lc, t_info, t_slot, hy, k_dp, k_right, k_node, total;
+    uint32_t unk_lc, unk_ro, nstart, bstart, bcur, binfo, udesc, desc, bpos, bcls, t_lc, t_info, t_slot, hy, k_dr, k_node,
+        tbytes, total;
 };
 
-static __host__ __device__ inline kp_fused_layout kp_fused_make_layout(uint32_t cap_c, uint32_t cap_k, uint32_t cap_r) {
+static __host__ __device__ inline kp_fused_layout kp_fused_make_layout(uint32_t cap_c, uint32_t cap_k, uint32_t cap_r,
+                                                                       uint32_t max_bytes) {
     kp_fused_layout L;
     const uint32_t C1 = cap_c + 2;
     uint32_t o = 0;
+    L.unk_lc = o; o += 4 * 64;
+    L.unk_ro = o; o += 4 * 64;
+    L.desc = o; o += 8 * C1;
+    L.k_dr = o; o += 8 * (cap_r + 1);
     L.nstart = o; o += 4 * C1;
     L.bstart = o; o += 4 * C1;
     L.bcur = o; o += 4 * C1;
     L.binfo = o; o += 4 * C1;
+    L.udesc = o; o += 4 * C1;
     L.t_lc = o; o += 4 * cap_k;
     L.t_info = o; o += 4 * cap_k;
-    L.k_dp = o; o += 4 * cap_r;
     o = (o + 7) & ~7u;
     L.t_slot = o; o += 2 * cap_k;
     L.hy = o; o += 2 * (cap_k / 2);
-    L.k_right = o; o += 2 * cap_r;
-    L.k_node = o; o += 2 * cap_r;
+    L.k_node = o; o += 2 * (cap_r + 1);
     L.bpos = o; o += 2 * C1;
     L.bcls = o; o += C1;
+    L.tbytes = o; o += max_bytes + 8;
     L.total = (o + 15) & ~15u;
     return L;
 }
 
-uint32_t kp_fused_smem_bytes(const kp_fused_class& k) { return kp_fused_make_layout(k.cap_c, k.cap_k, k.cap_r).total; }
+uint32_t kp_fused_smem_bytes(const kp_fused_class& k) {
+    return kp_fused_make_layout(k.cap_c, k.cap_k, k.cap_r, k.max_bytes).total;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Classification: one thread per sentence.  Sentences go to the list of the first class whose byte limit
@@ -147,49 +158,96 @@ struct kp_fused_args {
     const uint32_t* list;      // sentences of this class
     const uint32_t* count;     // how many
     uint32_t* cursor;          // ticket counter
-    uint32_t cap_c, cap_k, cap_r;
+    uint32_t cap_c, cap_k, cap_r, max_bytes;
     kp_token* stage;
     uint32_t* tcount;
     int32_t* eos_cost;
-    uint32_t* sel;             // sentences left to the pipeline ...
-    uint32_t* nsel;            // ... and how many
+    uint32_t* sel;             // sentences that do not fit this class: appended here (the largest class's list,
+    uint32_t* nsel;            // or, from the largest class, the pipeline's) ... and their count
     uint32_t* err;             // [0] invalid UTF-8
     unsigned long long* totals;   // [8] chars, [9] nodes (BOS and EOS included), [10] sentences done here
 };
 
+namespace {
+
+constexpr int WALKS = 3;       // start positions a lane walks at the same time (their gathers overlap)
+
+// One double-array walk in flight (da.rs:155-182).  `alive`: the transition into state q was in range and
+// nq = da[q] is loaded; the walk goes on while check[q] == prev.
+struct kp_walk {
+    uint32_t p, i, nch, nh;
+    int prev, q, c1;
+    int2 nq;
+    bool alive;
+};
+
+}  // namespace
+
 __global__ void __launch_bounds__(32) kp_fused(const kp_fused_args a, const kp_ddict d) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const kp_fused_layout L = kp_fused_make_layout(a.cap_c, a.cap_k, a.cap_r);
+    const kp_fused_layout L = kp_fused_make_layout(a.cap_c, a.cap_k, a.cap_r, a.max_bytes);
+    uint32_t* const unk_lc = (uint32_t*)(smem + L.unk_lc);
+    uint32_t* const unk_ro = (uint32_t*)(smem + L.unk_ro);
     uint32_t* const nstart = (uint32_t*)(smem + L.nstart);
     uint32_t* const bstart = (uint32_t*)(smem + L.bstart);
     uint32_t* const bcur = (uint32_t*)(smem + L.bcur);
     uint32_t* const binfo = (uint32_t*)(smem + L.binfo);
+    uint32_t* const udesc = (uint32_t*)(smem + L.udesc);
+    uint2* const desc = (uint2*)(smem + L.desc);
     uint16_t* const bpos = (uint16_t*)(smem + L.bpos);
     uint8_t* const bcls = smem + L.bcls;
     uint32_t* const t_lc = (uint32_t*)(smem + L.t_lc);
     uint32_t* const t_info = (uint32_t*)(smem + L.t_info);
     uint16_t* const t_slot = (uint16_t*)(smem + L.t_slot);
     uint16_t* const hy = (uint16_t*)(smem + L.hy);
-    int* const k_dp = (int*)(smem + L.k_dp);
-    uint32_t* const hx = (uint32_t*)(smem + L.k_dp);
-    uint16_t* const k_right = (uint16_t*)(smem + L.k_right);
+    int2* const k_dr = (int2*)(smem + L.k_dr);
+    uint32_t* const hx = (uint32_t*)(smem + L.k_dr);
     uint16_t* const k_node = (uint16_t*)(smem + L.k_node);
     uint2* const path = (uint2*)(smem + L.t_slot);
+    uint8_t* const tb = smem + L.tbytes;
     __shared__ uint32_t sh_hits;
     const uint32_t lane = lane_id();
     const uint32_t n_list = *a.count;
     const uint32_t cap_h = a.cap_k / 2;
+    const int16_t* const connT = d.connT;
+    const uint32_t stride = d.connT_stride;
 
-    while (true) {
-        uint32_t ticket = 0;
-        if (lane == 0) ticket = atomicAdd(a.cursor, 1u);
-        ticket = __shfl_sync(KP_FULL, ticket, 0);
-        if (ticket >= n_list) return;
+    // the unknown morphs, once per block
+    for (uint32_t u = lane; u < 64; u += 32) {
+        uint2 m = make_uint2(0u, 0u);
+        if (u < d.n_unk_morphs) m = ld_morph(d.unk_morphs, u);
+        unk_lc[u] = (m.x & 0xFFFFu) | (m.y << 16);
+        unk_ro[u] = (m.x >> 16) * stride;
+    }
+    uint32_t ticket = 0;
+    if (lane == 0) ticket = atomicAdd(a.cursor, 1u);
+    ticket = __shfl_sync(KP_FULL, ticket, 0);
+
+    while (ticket < n_list) {
         const uint32_t s = a.list[ticket];
+        if (lane == 0) ticket = atomicAdd(a.cursor, 1u);          // the next sentence's ticket, a whole sentence ahead
         const uint32_t lo = (uint32_t)(a.off[s] - a.base), hi = (uint32_t)(a.off[s + 1] - a.base);
         const uint32_t nbytes = hi - lo;
-        const uint8_t* const text = a.text + lo;
         bool give_up = false;                       // does not fit: the pipeline takes the sentence
+
+        // ---- the sentence's bytes into shared memory (loads of a batch in flight together) ----
+        {
+            const uint8_t* const text = a.text + lo;
+            for (uint32_t i0 = 0; i0 < nbytes; i0 += 256) {
+                uint32_t c[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint32_t i = i0 + 32 * k + lane;
+                    c[k] = i < nbytes ? text[i] : 0u;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint32_t i = i0 + 32 * k + lane;
+                    if (i < nbytes) tb[i] = (uint8_t)c[k];
+                }
+            }
+        }
+        __syncwarp();
 
         // ---- decode: UTF-8 validation (the C ABI must check what &str guarantees), char offsets, classes ----
         uint32_t n = 0;
@@ -199,7 +257,7 @@ __global__ void __launch_bounds__(32) kp_fused(const kp_fused_args a, const kp_d
             for (uint32_t i0 = 0; i0 < nbytes; i0 += 32) {
                 const uint32_t i = i0 + lane;
                 const bool inr = i < nbytes;
-                const uint32_t c = inr ? text[i] : 0x80u;
+                const uint32_t c = inr ? tb[i] : 0x80u;
                 const bool st = inr && !is_cont(c);
                 if (inr && !st) conts++;
                 const uint32_t m = __ballot_sync(KP_FULL, st);
@@ -211,7 +269,7 @@ __global__ void __launch_bounds__(32) kp_fused(const kp_fused_args a, const kp_d
                         uint32_t cp = c;
                         if (len > 1) {
                             claimed += len - 1;
-                            const uint32_t c1 = text[i + 1];
+                            const uint32_t c1 = tb[i + 1];
                             uint32_t lo1 = 0x80u, hi1 = 0xBFu;
                             if (c == 0xE0u) lo1 = 0xA0u;
                             if (c == 0xEDu) hi1 = 0x9Fu;
@@ -220,11 +278,11 @@ __global__ void __launch_bounds__(32) kp_fused(const kp_fused_args a, const kp_d
                             if (c1 < lo1 || c1 > hi1) bad = true;
                             if (len == 2) cp = ((c & 0x1Fu) << 6) | (c1 & 0x3Fu);
                             else {
-                                const uint32_t c2 = text[i + 2];
+                                const uint32_t c2 = tb[i + 2];
                                 if (!is_cont(c2)) bad = true;
                                 if (len == 3) cp = ((c & 0x0Fu) << 12) | ((c1 & 0x3Fu) << 6) | (c2 & 0x3Fu);
                                 else {
-                                    const uint32_t c3 = text[i + 3];
+                                    const uint32_t c3 = tb[i + 3];
                                     if (!is_cont(c3)) bad = true;
                                     cp = ((c & 0x07u) << 18) | ((c1 & 0x3Fu) << 12) | ((c2 & 0x3Fu) << 6) | (c3 & 0x3Fu);
                                 }
@@ -246,6 +304,7 @@ __global__ void __launch_bounds__(32) kp_fused(const kp_fused_args a, const kp_d
                     atomicOr(&a.err[0], 1u);
                     a.tcount[s] = 0;
                 }
+                ticket = __shfl_sync(KP_FULL, ticket, 0);
                 continue;
             }
             if (n > a.cap_c) give_up = true;
@@ -275,7 +334,7 @@ __global__ void __launch_bounds__(32) kp_fused(const kp_fused_args a, const kp_d
                 if (valid) {
                     const kp_catinfo ci = d.catinfo[cat];
                     const uint32_t uend = (ci.flags & 2u) ? min(runend, p + KP_MAX_UNKNOWN_LEN) : p + 1;
-                    binfo[p] = uend | (ci.unk_count << 11) | ((uint32_t)ci.unk_first << 16);
+                    binfo[p] = uend | (ci.unk_count << 11) | (((uint32_t)ci.unk_first & 0xFFu) << 16) | ((ci.flags & 1u) << 24);
                 }
             }
             if (lane == 0) {
@@ -284,73 +343,115 @@ __global__ void __launch_bounds__(32) kp_fused(const kp_fused_args a, const kp_d
             }
             __syncwarp();
 
-            // ---- walk: lane = start position (da.rs:155-182; the production walk of kp_lattice_count) ----
-            for (uint32_t p0 = 0; p0 < n; p0 += 32) {
-                const uint32_t p = p0 + lane;
-                if (p < n) {
-                    uint32_t nh = 0;
-                    if (d.da_len > KP_ROOT_ID) {
-                        uint32_t i = bpos[p];
-                        const uint32_t c = text[i];
-                        int prev = KP_ROOT_ID, q = 0;
-                        int2 nq = make_int2(0, 0);
-                        bool alive = false;
-                        int2 f = make_int2(KP_FIRST_SLOW, 0);
-                        if (c < 0xF0u) {
-                            uint32_t cp = c, len = 1;
-                            if (c >= 0xE0u) { cp = ((c & 0x0Fu) << 12) | ((text[i + 1] & 0x3Fu) << 6) | (text[i + 2] & 0x3Fu); len = 3; }
-                            else if (c >= 0x80u) { cp = ((c & 0x1Fu) << 6) | (text[i + 1] & 0x3Fu); len = 2; }
-                            f = d.first[cp];
-                            if (f.x != KP_FIRST_SLOW) {          // arrive in state f.x as if by the character's last byte
-                                i += len - 1;
-                                q = f.x;
-                                alive = f.x >= 0;
-                                nq = make_int2(f.y, 0);
-                                prev = 0;
-                            }
-                        }
-                        if (f.x == KP_FIRST_SLOW) {
-                            q = d.da[KP_ROOT_ID].x + (int)c;                                 // da.rs:160
-                            alive = (uint32_t)q < d.da_len;                                  // Vec::get -> None (da.rs:161)
-                            if (alive) nq = d.da[q];
-                        }
-                        uint32_t nch = 1;            // chars among the bytes consumed, the one being tried included
-                        int c1 = i + 1 < nbytes ? (int)(int8_t)text[i + 1] : 0;
-                        while (alive && nq.y == prev) {                                      // da.rs:162-164
-                            const int ahead = nq.x;                                          // + TERMINATOR (0), da.rs:165
-                            const int q2 = nq.x + (c1 & 0xFF);
-                            const uint32_t i2 = i + 1;
-                            const bool pa = (uint32_t)ahead < d.da_len && (c1 >= -64 || d.mid_char_keys);
-                            const bool p2 = i2 < nbytes && (uint32_t)q2 < d.da_len;
-                            int2 na = make_int2(0, 0), nq2 = make_int2(0, 0);
-                            if (pa) na = d.da[ahead];
-                            if (p2) nq2 = d.da[q2];
-                            int c2 = 0;
-                            if (i2 + 1 < nbytes) c2 = (int)(int8_t)text[i2 + 1];
-                            if (pa && na.y == q && na.x < 0) {                               // da.rs:167-174
-                                const uint32_t id = (uint32_t)(-na.x);
-                                const uint32_t h = atomicAdd(&sh_hits, 1u);
-                                if (h < cap_h && nch <= MAX_NCH) {
-                                    hx[h] = id;
-                                    hy[h] = (uint16_t)(p | (nch << 10));
-                                } else {
-                                    atomicOr(&sh_hits, 0x80000000u);                         // does not fit
+            // ---- walk: WALKS start positions per lane at a time (da.rs:155-182; the walk of kp_lattice_count) ----
+            if (d.da_len > KP_ROOT_ID) {
+                const int root_base = d.da[KP_ROOT_ID].x;
+                for (uint32_t p0 = 0; p0 < n; p0 += 32 * WALKS) {
+                    kp_walk w[WALKS];
+#pragma unroll
+                    for (int k = 0; k < WALKS; k++) {
+                        kp_walk& x = w[k];
+                        x.p = p0 + 32 * k + lane;
+                        x.nh = 0;
+                        x.alive = false;
+                        x.nch = 1;
+                        x.prev = KP_ROOT_ID;
+                        x.q = 0;
+                        x.nq = make_int2(0, 0);
+                        x.c1 = 0;
+                        x.i = 0;
+                        if (x.p < n) {
+                            uint32_t i = bpos[x.p];
+                            const uint32_t c = tb[i];
+                            int2 f = make_int2(KP_FIRST_SLOW, 0);
+                            if (c < 0xF0u) {
+                                uint32_t cp = c, len = 1;
+                                if (c >= 0xE0u) { cp = ((c & 0x0Fu) << 12) | ((tb[i + 1] & 0x3Fu) << 6) | (tb[i + 2] & 0x3Fu); len = 3; }
+                                else if (c >= 0x80u) { cp = ((c & 0x1Fu) << 6) | (tb[i + 1] & 0x3Fu); len = 2; }
+                                f = d.first[cp];
+                                if (f.x != KP_FIRST_SLOW) {          // arrive in state f.x as if by the character's last byte
+                                    i += len - 1;
+                                    x.q = f.x;
+                                    x.alive = f.x >= 0;
+                                    x.nq = make_int2(f.y, 0);
+                                    x.prev = 0;
                                 }
-                                nh++;
                             }
-                            nch += c1 >= -64;            // the byte tried next starts a character
-                            prev = q;
-                            q = q2;
-                            nq = nq2;
-                            alive = p2;
-                            c1 = c2;
-                            i = i2;
+                            if (f.x == KP_FIRST_SLOW) {
+                                x.q = root_base + (int)c;                                        // da.rs:160
+                                x.alive = (uint32_t)x.q < d.da_len;                              // Vec::get -> None (da.rs:161)
+                                if (x.alive) x.nq = d.da[x.q];
+                            }
+                            x.i = i;
+                            x.c1 = i + 1 < nbytes ? (int)(int8_t)tb[i + 1] : 0;
+                        }
+                    }
+                    while (true) {
+                        bool any = false;
+#pragma unroll
+                        for (int k = 0; k < WALKS; k++) {
+                            kp_walk& x = w[k];
+                            x.alive = x.alive && x.nq.y == x.prev;                               // da.rs:162-164
+                            any = any || x.alive;
+                        }
+                        if (!any) break;
+                        int2 na[WALKS], nq2[WALKS];
+                        bool pa[WALKS], p2[WALKS];
+                        int q2[WALKS];
+#pragma unroll
+                        for (int k = 0; k < WALKS; k++) {                                        // all gathers of the step first
+                            kp_walk& x = w[k];
+                            const int ahead = x.nq.x;                                            // + TERMINATOR (0), da.rs:165
+                            q2[k] = x.nq.x + (x.c1 & 0xFF);
+                            pa[k] = x.alive && (uint32_t)ahead < d.da_len && (x.c1 >= -64 || d.mid_char_keys);
+                            p2[k] = x.alive && x.i + 1 < nbytes && (uint32_t)q2[k] < d.da_len;
+                            na[k] = make_int2(0, 0);
+                            nq2[k] = make_int2(0, 0);
+                            if (pa[k]) na[k] = d.da[ahead];
+                            if (p2[k]) nq2[k] = d.da[q2[k]];
+                        }
+#pragma unroll
+                        for (int k = 0; k < WALKS; k++) {
+                            kp_walk& x = w[k];
+                            if (x.alive) {
+                                if (pa[k] && na[k].y == x.q && na[k].x < 0) {                    // da.rs:167-174
+                                    const uint32_t id = (uint32_t)(-na[k].x);
+                                    const uint32_t h = atomicAdd(&sh_hits, 1u);
+                                    if (h < cap_h && x.nch <= MAX_NCH) {
+                                        hx[h] = id;
+                                        hy[h] = (uint16_t)(x.p | (x.nch << 10));
+                                    } else {
+                                        atomicOr(&sh_hits, 0x80000000u);                         // does not fit
+                                    }
+                                    x.nh++;
+                                }
+                                x.nch += x.c1 >= -64;        // the byte tried next starts a character
+                                x.prev = x.q;
+                                x.q = q2[k];
+                                x.nq = nq2[k];
+                                x.alive = p2[k];
+                                x.i++;
+                                x.c1 = x.i + 1 < nbytes ? (int)(int8_t)tb[x.i + 1] : 0;
+                            }
                         }
                     }
                     // unknown words (lattice.rs:42-99): when nothing matched, or the class always invokes them
-                    const kp_catinfo ci = d.catinfo[bcls[p]];
-                    if ((nh == 0 || (ci.flags & 1u)) && ci.unk_count) {
-                        const uint32_t bi = binfo[p];
+#pragma unroll
+                    for (int k = 0; k < WALKS; k++) {
+                        const kp_walk& x = w[k];
+                        if (x.p < n) {
+                            const uint32_t bi = binfo[x.p];
+                            if ((x.nh == 0 || (bi >> 24)) && ((bi >> 11) & 31u)) {
+                                binfo[x.p] = bi | (1u << 10);
+                                atomicOr(&bcur[bi & 1023u], 0x80000000u);
+                            }
+                        }
+                    }
+                }
+            } else {
+                for (uint32_t p = lane; p < n; p += 32) {
+                    const uint32_t bi = binfo[p];
+                    if ((bi >> 11) & 31u) {
                         binfo[p] = bi | (1u << 10);
                         atomicOr(&bcur[bi & 1023u], 0x80000000u);
                     }
@@ -379,6 +480,7 @@ __global__ void __launch_bounds__(32) kp_fused(const kp_fused_args a, const kp_d
         if (!give_up) {
             // exclusive scans over the boundaries 0..n: first node of every start, first slot of every bucket
             uint32_t ca = 0, cb = 0;
+            bool wide = false;
             for (uint32_t q0 = 0; q0 <= n; q0 += 32) {
                 const uint32_t q = q0 + lane;
                 uint32_t va = 0, vb = 0;
@@ -387,6 +489,7 @@ __global__ void __launch_bounds__(32) kp_fused(const kp_fused_args a, const kp_d
                     const uint32_t bc = bcur[q];
                     vb = (bc & 0x7FFFFFFFu) + (q == 0 ? 1u : 0u);                 // + BOS in edges[0] (lattice.rs:156-164)
                     if (bc >> 31) vb += (binfo[q - 1] >> 11) & 31u;               // shared slots: the ids of the class before q
+                    if (va > 900u) wide = true;                                   // desc carries 10-bit target counts
                 }
                 uint32_t xa = va, xb = vb;
                 for (int o = 1; o < 32; o <<= 1) {
@@ -406,163 +509,174 @@ __global__ void __launch_bounds__(32) kp_fused(const kp_fused_args a, const kp_d
             }
             n_known = ca;
             n_slots = cb;
-            if (n_known > a.cap_k || n_slots > a.cap_r) give_up = true;
+            if (n_known > a.cap_k || n_slots > a.cap_r || __any_sync(KP_FULL, wide)) give_up = true;
         }
         if (give_up) {
             if (lane == 0) a.sel[atomicAdd(a.nsel, 1u)] = s;
+            ticket = __shfl_sync(KP_FULL, ticket, 0);
             continue;
         }
         if (lane == 0) bstart[n + 1] = n_slots;
         __syncwarp();
 
-        // ---- expand: one lane per hit; a known node {left, cost, id} at its start, {right, node} at its end ----
+        // ---- expand, pass 1: one lane per hit hands out node indices and bucket slots (lattice.rs:177-188) ----
         if (lane == 0) {
             const uint32_t i = nstart[n];
             nstart[n] = i + 1;
-            t_lc[i] = 0;                            // EOS: morph (0,0,0)
-            t_info[i] = EOS_INFO;
-            t_slot[i] = (uint16_t)NONE16;           // ends nowhere
+            t_info[i] = EOS_INFO;                   // EOS: morph (0,0,0); it ends nowhere: its dp parks in slot n_slots
+            t_slot[i] = (uint16_t)n_slots;
         }
-        const uint32_t H = sh_hits;
-        for (uint32_t h = lane; h < H; h += 32) {
-            const uint32_t x = hx[h], y = hy[h];
-            const uint32_t id = x & ID_MASK20, k = x >> ID_BITS, p = y & 1023u, nch = y >> 10;
-            const uint32_t i0 = atomicAdd(&nstart[p], k);
-            const uint32_t s0 = atomicAdd(&bcur[p + nch], k);
-            for (uint32_t dd = 0; dd < k; dd++) {                                 // lattice.rs:177-188
-                const uint2 m = ld_morph(d.morphs, id + dd - 1);
-                t_lc[i0 + dd] = (m.x & 0xFFFFu) | (m.y << 16);
-                t_info[i0 + dd] = (id + dd) | (nch << ID_BITS);
-                t_slot[i0 + dd] = (uint16_t)(s0 + dd);
-                k_right[s0 + dd] = (uint16_t)(m.x >> 16);
-                k_node[s0 + dd] = (uint16_t)(i0 + dd);
+        {
+            const uint32_t H = sh_hits;
+            for (uint32_t h = lane; h < H; h += 32) {
+                const uint32_t x = hx[h], y = hy[h];
+                const uint32_t id = x & ID_MASK20, k = x >> ID_BITS, p = y & 1023u, nch = y >> 10;
+                const uint32_t i0 = atomicAdd(&nstart[p], k);
+                const uint32_t s0 = atomicAdd(&bcur[p + nch], k);
+                for (uint32_t dd = 0; dd < k; dd++) {
+                    t_info[i0 + dd] = (id + dd) | (nch << ID_BITS);
+                    t_slot[i0 + dd] = (uint16_t)(s0 + dd);
+                }
             }
         }
-        __syncwarp();                               // the hits are dead from here on: k_dp takes their place
-        // shared slots of the unknown ids: [bcur[e], bstart[e + 1]); BOS: dp None -> unwrap_or(0) (lattice.rs:127)
+        __syncwarp();                               // the hits are dead from here on: k_dr takes their place
+        // pass 2: one lane per node fetches its morph: {left, cost} at the node, {right} at its slot (two in flight)
+        for (uint32_t i0 = 0; i0 < n_known; i0 += 64) {
+            const uint32_t ia = i0 + lane, ib = i0 + 32 + lane;
+            const uint32_t fa = ia < n_known ? t_info[ia] : EOS_INFO, fb = ib < n_known ? t_info[ib] : EOS_INFO;
+            uint2 ma = make_uint2(0u, 0u), mb = make_uint2(0u, 0u);
+            if (fa != EOS_INFO) ma = ld_morph(d.morphs, (fa & ID_MASK20) - 1);
+            if (fb != EOS_INFO) mb = ld_morph(d.morphs, (fb & ID_MASK20) - 1);
+            if (ia < n_known) {
+                t_lc[ia] = (ma.x & 0xFFFFu) | (ma.y << 16);
+                if (fa != EOS_INFO) {
+                    const uint32_t sl = t_slot[ia];
+                    k_dr[sl].y = (int)((ma.x >> 16) * stride);
+                    k_node[sl] = (uint16_t)ia;
+                }
+            }
+            if (ib < n_known) {
+                t_lc[ib] = (mb.x & 0xFFFFu) | (mb.y << 16);
+                if (fb != EOS_INFO) {
+                    const uint32_t sl = t_slot[ib];
+                    k_dr[sl].y = (int)((mb.x >> 16) * stride);
+                    k_node[sl] = (uint16_t)ib;
+                }
+            }
+        }
+        // shared slots of the unknown ids: [bcur[e], bstart[e + 1]); BOS: dp None -> unwrap_or(0) (lattice.rs:127);
+        // and the per-boundary descriptors of the sweep
+        uint32_t n_unknown = 0;
         for (uint32_t e = lane; e <= n; e += 32) {
             const uint32_t q0 = bcur[e], q1 = bstart[e + 1];
             if (q1 > q0) {
-                const uint32_t first = binfo[e - 1] >> 16;
+                const uint32_t first = (binfo[e - 1] >> 16) & 0xFFu;
                 for (uint32_t q = q0; q < q1; q++) {
-                    k_right[q] = (uint16_t)(ld_morph(d.unk_morphs, first + (q - q0) - 1).x >> 16);
-                    k_dp[q] = INT_MAX;
+                    k_dr[q] = make_int2(INT_MAX, (int)unk_ro[first + (q - q0) - 1]);
                     k_node[q] = 0;
                 }
             }
             if (e == 0) {
-                k_dp[0] = 0;
-                k_right[0] = 0;
+                k_dr[0] = make_int2(0, 0);
                 k_node[0] = (uint16_t)NONE16;
             }
-        }
-        __syncwarp();
-
-        // ---- sweep (lattice.rs:116-143): per boundary, lanes = (target, slice of the predecessors) ----
-        int eos_dp = KP_INF;
-        uint32_t n_unknown = 0;
-        for (uint32_t p = 0; p <= n; p++) {
-            const uint32_t t0 = p ? nstart[p - 1] : 0u, Tk = nstart[p] - t0;
-            const uint32_t bi = binfo[p];
+            const uint32_t t0 = e ? nstart[e - 1] : 0u, Tk = nstart[e] - t0;
+            const uint32_t bi = binfo[e];
             const uint32_t Tu = (bi >> 10) & 1u ? (bi >> 11) & 31u : 0u;
             const uint32_t T = Tk + Tu;
             n_unknown += Tu;
-            if (T == 0) continue;
-            const uint32_t r0 = bstart[p], R = bstart[p + 1] - r0;
             uint32_t sh = T <= 1 ? 0u : 32u - (uint32_t)__clz(T - 1);
             if (sh > 5) sh = 5;
-            const uint32_t W = 1u << sh, J = 32u >> sh;          // targets per pass, predecessor slices
-            const uint32_t il = lane & (W - 1), jo = lane >> sh;
-            const uint32_t ufirst = bi >> 16, ushared = bcur[bi & 1023u];
-            for (uint32_t tc = 0; tc < T; tc += W) {
+            desc[e] = make_uint2(t0 | (Tk << 12) | (T << 22), bstart[e] | ((q1 - bstart[e]) << 12) | (sh << 24));
+            udesc[e] = bcur[bi & 1023u] | (bi & 0x00FF0000u);
+        }
+        n_unknown = __reduce_add_sync(KP_FULL, n_unknown);
+        __syncwarp();
+
+        // ---- sweep (lattice.rs:116-143): per boundary, lanes = (target, slice of the predecessors) ----
+        // B0 stands for "no predecessor seen": every real dp_j + conn is below it, and B0 + cost >= INF for every cost
+        constexpr int B0 = KP_INF + 32768;
+        for (uint32_t p = 0; p <= n; p++) {
+            const uint2 ds = desc[p];
+            const uint32_t T = ds.x >> 22;
+            if (T == 0) continue;
+            const uint32_t t0 = ds.x & 0xFFFu, Tk = (ds.x >> 12) & 0x3FFu;
+            const uint32_t R = (ds.y >> 12) & 0xFFFu, sh = ds.y >> 24;
+            const int2* const bucket = k_dr + (ds.y & 0xFFFu);
+            const uint32_t ud = udesc[p];
+            const uint32_t il = lane & ((1u << sh) - 1u), jo = lane >> sh, J = 32u >> sh;
+            for (uint32_t tc = 0; tc < T; tc += 1u << sh) {
                 const uint32_t ti = tc + il;
-                const bool tv = ti < T;
-                uint32_t lc = 0;
-                if (tv) {
-                    if (ti < Tk) lc = t_lc[t0 + ti];
-                    else {
-                        const uint2 m = ld_morph(d.unk_morphs, ufirst + (ti - Tk) - 1);   // lattice.rs:195
-                        lc = (m.x & 0xFFFFu) | (m.y << 16);
-                    }
+                const bool tv = ti < T, unk = ti >= Tk;
+                const uint32_t* const src = unk ? unk_lc + ((ud >> 16) + (ti - Tk) - 1) : t_lc + (t0 + ti);
+                const uint32_t lc = tv ? *src : 0u;
+                const int16_t* const col = connT + (lc & 0xFFFFu);
+                int best = B0;
+                const uint32_t Rl = tv ? R : 0u;
+                for (uint32_t j = jo; j < Rl; j += J) {
+                    const int2 e = bucket[j];
+                    best = __viaddmin_s32(e.x, (int)__ldg(col + e.y), best);      // connection.rs:12-14
                 }
-                const uint32_t left = lc & 0xFFFFu;
-                int best = INT_MAX;
-                if (tv)
-                    for (uint32_t j = jo; j < R; j += J) {
-                        const int dpj = k_dp[r0 + j];
-                        const int cell = ld_cell(d.connT, k_right[r0 + j], d.connT_stride, left);   // connection.rs:12-14
-                        best = __viaddmin_s32(dpj, cell, best);
-                    }
-                for (uint32_t o = 16; o >= W; o >>= 1) best = min(best, __shfl_xor_sync(KP_FULL, best, o));
+                if (sh < 5) best = min(best, __shfl_xor_sync(KP_FULL, best, 16));
+                if (sh < 4) best = min(best, __shfl_xor_sync(KP_FULL, best, 8));
+                if (sh < 3) best = min(best, __shfl_xor_sync(KP_FULL, best, 4));
+                if (sh < 2) best = min(best, __shfl_xor_sync(KP_FULL, best, 2));
+                if (sh < 1) best = min(best, __shfl_xor_sync(KP_FULL, best, 1));
                 if (tv && jo == 0) {
-                    int dp = KP_INF;
-                    if (R) dp = min(best + (int)(int16_t)(lc >> 16), KP_INF);            // lattice.rs:127-139
-                    if (ti < Tk) {
-                        const uint32_t slot = t_slot[t0 + ti];
-                        if (slot == NONE16) eos_dp = dp;
-                        else k_dp[slot] = dp;
-                    } else {
-                        const uint32_t q = ushared + (ti - Tk);
-                        if (dp < k_dp[q]) {           // strict: the first minimal start is kept
-                            k_dp[q] = dp;
-                            k_node[q] = (uint16_t)p;
-                        }
+                    const int dp = min(best + (int)(int16_t)(lc >> 16), KP_INF);          // lattice.rs:127-139
+                    const uint32_t dst = unk ? (ud & 0xFFFFu) + (ti - Tk) : t_slot[t0 + ti];
+                    const int old = unk ? k_dr[dst].x : INT_MAX;
+                    if (dp < old) {                   // unknown: strict, the first minimal start is kept
+                        k_dr[dst].x = dp;
+                        if (unk) k_node[dst] = (uint16_t)p;
                     }
                 }
             }
             __syncwarp();
         }
-        eos_dp = __shfl_sync(KP_FULL, eos_dp, 0);     // EOS is the only target of boundary n: lane 0 held it
+        const int eos_dp = k_dr[n_slots].x;
 
-        // ---- back-trace (lattice.rs:144-153): the first predecessor attaining dp, by (start, kind, id) ----
+        // ---- back-trace (lattice.rs:144-153): the first predecessor attaining dp, in `edges` order: ascending
+        // start, known before unknown, ascending id = ascending (start, slot) ----
         uint32_t cnt = 0;
         {
             uint32_t cur_id = 0, cur_kind = KP_CLASS_DUMMY, cur_p = n, cur_len = 3, left = 0;
             int cost = 0, dpc = eos_dp;
-            while (true) {
-                if (dpc >= KP_INF) break;            // pre_nodes[pos] is None
+            while (dpc < KP_INF) {                   // pre_nodes[pos] is None otherwise
                 const int want = dpc - cost;
-                const uint32_t r0 = bstart[cur_p], r1 = bstart[cur_p + 1], rs = bcur[cur_p];
-                const uint32_t sfirst = cur_p ? binfo[cur_p - 1] >> 16 : 0u;
-                uint32_t best_key = 0xFFFFFFFFu, best_j = 0;
-                for (uint32_t j0 = r0; j0 < r1; j0 += 32) {
+                const uint2 ds = desc[cur_p];
+                const uint32_t r0 = ds.y & 0xFFFu, R = (ds.y >> 12) & 0xFFFu, rs = bcur[cur_p];
+                const int16_t* const col = connT + left;
+                uint32_t best_key = 0xFFFFFFFFu;
+                for (uint32_t j0 = 0; j0 < R; j0 += 32) {
                     const uint32_t j = j0 + lane;
                     uint32_t key = 0xFFFFFFFFu;
-                    if (j < r1) {
-                        const int dpj = k_dp[j];
-                        if (dpj != INT_MAX && dpj + ld_cell(d.connT, k_right[j], d.connT_stride, left) == want) {
-                            const uint32_t nd = k_node[j];
-                            if (j >= rs) key = (nd << 22) | ((uint32_t)KP_CLASS_UNKNOWN << ID_BITS) | (sfirst + (j - rs));
-                            else if (nd == NONE16) key = 0;                       // BOS
-                            else {
-                                const uint32_t inf = t_info[nd];
-                                key = ((cur_p - (inf >> ID_BITS)) << 22) | ((uint32_t)KP_CLASS_KNOWN << ID_BITS) | (inf & ID_MASK20);
-                            }
+                    if (j < R) {
+                        const int2 e = k_dr[r0 + j];
+                        if (e.x != INT_MAX && e.x + (int)__ldg(col + e.y) == want) {
+                            const uint32_t nd = k_node[r0 + j];
+                            uint32_t start = nd;                                  // shared slot: its first minimal start
+                            if (r0 + j < rs) start = nd == NONE16 ? 0u : cur_p - (t_info[nd] >> ID_BITS);
+                            key = (start << 12) | j;
                         }
                     }
-                    const uint32_t kmin = __reduce_min_sync(KP_FULL, key);
-                    if (kmin < best_key) {
-                        best_key = kmin;
-                        const uint32_t src = (uint32_t)__ffs(__ballot_sync(KP_FULL, key == kmin)) - 1;
-                        best_j = __shfl_sync(KP_FULL, j, src);
-                    }
+                    best_key = min(best_key, __reduce_min_sync(KP_FULL, key));
                 }
                 if (best_key == 0xFFFFFFFFu) break;  // unreachable for a consistent dp table
-                __syncwarp();
                 if (lane == 0) path[cnt] = make_uint2(cur_id | (cur_kind << 30), cur_p | (cur_len << 16));
                 cnt++;
-                if (best_key == 0) break;            // BOS: no predecessor, not emitted
-                // the chosen node becomes the current one
-                const uint32_t nd = k_node[best_j];
-                dpc = k_dp[best_j];
-                if (best_j >= rs) {
+                const uint32_t bj = r0 + (best_key & 0xFFFu);
+                const uint32_t nd = k_node[bj];
+                if (bj < rs && nd == NONE16) break;  // BOS: no predecessor, not emitted
+                dpc = k_dr[bj].x;
+                if (bj >= rs) {                      // the class's unknown id (bj - rs), started at nd
+                    cur_id = ((binfo[cur_p - 1] >> 16) & 0xFFu) + (bj - rs);
+                    const uint32_t lc = unk_lc[cur_id - 1];
                     cur_kind = KP_CLASS_UNKNOWN;
-                    cur_id = sfirst + (best_j - rs);
                     cur_len = cur_p - nd;
                     cur_p = nd;
-                    const uint2 m = ld_morph(d.unk_morphs, cur_id - 1);
-                    left = m.x & 0xFFFFu;
-                    cost = (int)(int16_t)(m.y & 0xFFFFu);
+                    left = lc & 0xFFFFu;
+                    cost = (int)(int16_t)(lc >> 16);
                 } else {
                     const uint32_t inf = t_info[nd], lc = t_lc[nd];
                     cur_kind = KP_CLASS_KNOWN;
@@ -591,6 +705,7 @@ __global__ void __launch_bounds__(32) kp_fused(const kp_fused_args a, const kp_d
             // {id, position, start, char_len | cls << 16}; EOS: char_len = "EOS".chars().count()
             out[k] = make_uint4(e.x & KP_ID_MASK, bpos[p], p, (e.y >> 16) | (kind << 16));
         }
+        ticket = __shfl_sync(KP_FULL, ticket, 0);
         __syncwarp();
     }
 }
@@ -599,7 +714,7 @@ __global__ void __launch_bounds__(32) kp_fused(const kp_fused_args a, const kp_d
 // host side
 // ---------------------------------------------------------------------------------------------------------
 bool kp_fused_dict_ok(const kp_ddict& d, const kp_catinfo* host_catinfo) {
-    if (d.n_morphs >= (1u << ID_BITS) || d.n_unk_morphs >= 65536u || d.conn_col > 65536u || d.conn_row > 65536u) return false;
+    if (d.n_morphs >= (1u << ID_BITS) || d.n_unk_morphs > 64u || d.conn_col > 65536u || d.conn_row > 65536u) return false;
     for (int c = 0; c < 256; c++)
         if (host_catinfo[c].unk_count > 31u || (uint32_t)host_catinfo[c].unk_first + host_catinfo[c].unk_count > 65535u)
             return false;
@@ -649,7 +764,8 @@ int kp_launch_fused_classify(const kp_chunk& c, const kp_fused_classes& cls, uin
 }
 
 int kp_launch_fused(const kp_chunk& c, const kp_ddict& d, const kp_fused_class& k, const uint32_t* list,
-                    const uint32_t* count, uint32_t* cursor, uint32_t* nsel, uint32_t expected, cudaStream_t st) {
+                    const uint32_t* count, uint32_t* cursor, uint32_t* over_list, uint32_t* over_count, uint32_t expected,
+                    cudaStream_t st) {
     kp_fused_args a;
     a.text = c.text;
     a.off = c.off;
@@ -660,11 +776,12 @@ int kp_launch_fused(const kp_chunk& c, const kp_ddict& d, const kp_fused_class& 
     a.cap_c = k.cap_c;
     a.cap_k = k.cap_k;
     a.cap_r = k.cap_r;
+    a.max_bytes = k.max_bytes;
     a.stage = c.stage;
     a.tcount = c.tcount;
     a.eos_cost = c.eos_cost;
-    a.sel = (uint32_t*)c.sel_out;
-    a.nsel = nsel;
+    a.sel = over_list;
+    a.nsel = over_count;
     a.err = c.err;
     a.totals = (unsigned long long*)c.totals;
     uint32_t blocks = k.blocks;

@@ -113,5 +113,7 @@ int kp_fused_prepare(kp_fused_classes* cls, int device);
 // lists: [cls.n][S_all] sentence lists per class; counts: [cls.n]; nsel: sentences left to the pipeline (c.sel_out)
 int kp_launch_fused_classify(const kp_chunk& c, const kp_fused_classes& cls, uint32_t* lists, uint32_t* counts,
                              uint32_t* nsel, cudaStream_t st);
+// over_list / over_count: where the sentences that do not fit class k are appended
 int kp_launch_fused(const kp_chunk& c, const kp_ddict& d, const kp_fused_class& k, const uint32_t* list,
-                    const uint32_t* count, uint32_t* cursor, uint32_t* nsel, uint32_t expected, cudaStream_t st);
+                    const uint32_t* count, uint32_t* cursor, uint32_t* over_list, uint32_t* over_count, uint32_t expected,
+                    cudaStream_t st);

@@ -295,7 +295,8 @@ def product_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda:%d" % local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=4))
 
     def barrier():
         if world > 1:
@@ -342,16 +343,10 @@ def product_arm(args):
 
     # ---- token gather to rank 0 (north_star's second collective), INSIDE every timed step at N > 1 ----
     gather = None
-    if world > 1:
-        gather = sharded.TokenGather(dev, S, int(n_bytes * 0.2) + S)     # ~0.12 tokens per input byte
-
-    def gather_device_result(r):
-        t_off = sharded.device_view(r.tok_off, 4 * (S + 1), local)
-        t_tok = sharded.device_view(r.tokens, 8 * int(r.n_tokens), local)
-        t_eos = sharded.device_view(r.eos_cost, 4 * S, local)
-        return gather.gather(t_off, t_tok, t_eos)
-
-    ge0, ge1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:      # capacities are part of the block layout: the same on every rank (max over the ranks' batches)
+        caps = torch.tensor([S, int(n_bytes * 0.14) + S], dtype=torch.int64, device=dev)     # 0.12 tokens per input byte here
+        dist.all_reduce(caps, op=dist.ReduceOp.MAX)
+        gather = sharded.NcclGather(local, int(caps[0]), int(caps[1]))
 
     def step_device():
         """-> (result, device ms of the step: library stream events + the gather's events on torch's stream)."""
@@ -361,11 +356,8 @@ def product_arm(args):
         p = tk.profile()
         g, gms = None, 0.0
         if gather is not None:
-            ge0.record()
-            g = gather_device_result(r)
-            ge1.record()
-            torch.cuda.synchronize()
-            gms = ge0.elapsed_time(ge1)
+            g = gather.gather(r)
+            gms = gather.last_ms()
         return r, p, g, gms
 
     # exact work counters (outside any timed region)
@@ -453,21 +445,16 @@ def product_arm(args):
         hs_off = torch.from_numpy(sh_off.copy()).pin_memory()
         Ss, Bs = s1 - s0, int(sh_off[-1])
         cap_s = max(b - a for a, b in ranges)
-        cap_t = max(int((off0[b] - off0[a]) * 0.2) + (b - a) for a, b in ranges)
-        sg = sharded.TokenGather(dev, cap_s, cap_t)
+        cap_t = max(int((off0[b] - off0[a]) * 0.14) + (b - a) for a, b in ranges)
+        sg = sharded.NcclGather(local, cap_s, cap_t)
 
         def step_strong():
             flush.zero_()
             torch.cuda.synchronize()
             rr = tk.tokenize_batch_device8(ds_text.data_ptr(), ds_off.data_ptr(), Ss, 0, Bs)
             pm = tk.profile()["total_ms"]
-            ge0.record()
-            gg = sg.gather(sharded.device_view(rr.tok_off, 4 * (Ss + 1), local),
-                           sharded.device_view(rr.tokens, 8 * int(rr.n_tokens), local),
-                           sharded.device_view(rr.eos_cost, 4 * Ss, local))
-            ge1.record()
-            torch.cuda.synchronize()
-            return gg, pm, ge0.elapsed_time(ge1)
+            gg = sg.gather(rr)
+            return gg, pm, sg.last_ms()
 
         for _ in range(args.warmup):
             step_strong()
@@ -496,7 +483,7 @@ def product_arm(args):
                   "e2e_value": int(off0[-1]) * args.steps / (strong_e2e_ms * 1e-3),
                   "what": "BASELINE.json configs[4]: one batch split into %d byte-balanced contiguous shards, shard text "
                           "resident in HBM; every timed step = tokenize the shard + NCCL gather of the token records on "
-                          "rank 0 (one torch.distributed gather over NVLink); device time, max over ranks.  e2e_value: "
+                          "rank 0 (kp_gather_tokens over NVLink); device time, max over ranks.  e2e_value: "
                           "every rank's kp_queue on its shard from pinned host memory to pinned host memory" % world}
 
     # ---- reduce over ranks: bytes summed, times max ------------------------------------------------
@@ -517,10 +504,17 @@ def product_arm(args):
         cores, _ = host_info()
         ref = oracle_reference(text, off, cores)
         checks = {}
-        checks["device"] = compare_with_oracle(ref, dev_result[0], expand_tokens8(dev_result[0], dev_result[1], off),
-                                               dev_result[2])
-        checks["e2e_queue"] = compare_with_oracle(ref, e2e_result[0], expand_tokens8(e2e_result[0], e2e_result[1], off),
-                                                  e2e_result[2])
+
+        def guarded(fn):          # a malformed result must fail the comparison, not leave the other ranks waiting
+            try:
+                return fn()
+            except Exception as e:   # noqa: BLE001
+                return "comparison raised %s: %s" % (type(e).__name__, e)
+
+        checks["device"] = guarded(lambda: compare_with_oracle(
+            ref, dev_result[0], expand_tokens8(dev_result[0], dev_result[1], off), dev_result[2]))
+        checks["e2e_queue"] = guarded(lambda: compare_with_oracle(
+            ref, e2e_result[0], expand_tokens8(e2e_result[0], e2e_result[1], off), e2e_result[2]))
         sentences = S
         if world > 1:
             # rank 0 holds the gathered results: the weak one over all ranks' batches, the strong one over batch 0
@@ -536,10 +530,12 @@ def product_arm(args):
                     g_offs.append(of[1:] + g_offs[-1][-1])
                 g_offv = np.concatenate(g_offs)
                 gref = oracle_reference(g_text, g_offv, cores)
-                gb = sharded.to_batch_result(*g_last, g_offv)
-                checks["gathered_weak"] = compare_with_oracle(gref, gb.tok_off, gb.tokens, gb.eos_cost)
-                sb = sharded.to_batch_result(*g_strong, off0)
-                checks["gathered_strong"] = compare_with_oracle(ref, sb.tok_off, sb.tokens, sb.eos_cost)
+                gw = gather.to_host(g_last)
+                checks["gathered_weak"] = guarded(lambda: compare_with_oracle(
+                    gref, gw[0], expand_tokens8(gw[0], gw[1], g_offv), gw[2]))
+                gs = sg.to_host(g_strong)
+                checks["gathered_strong"] = guarded(lambda: compare_with_oracle(
+                    ref, gs[0], expand_tokens8(gs[0], gs[1], off0), gs[2]))
                 sentences = len(g_offv) - 1
         bad = {k: v for k, v in checks.items() if v}
         flag = torch.tensor([1.0 if bad else 0.0], device=dev)
@@ -581,8 +577,8 @@ def product_arm(args):
                                        "of the token records on rank 0" % world),
                        "path": args.path,
                        "l2": "flushed between steps (256 MiB memset outside the timed events)",
-                       "timing": "CUDA events: the library stream around each whole step plus, at N > 1, torch's stream "
-                                 "around the token gather; summed over steps, max over ranks"},
+                       "timing": "CUDA events: the library stream around each whole step plus, at N > 1, the gather's stream "
+                                 "around kp_gather_tokens; summed over steps, max over ranks"},
             "wall_ms_per_step": wall_ms / K,
             "e2e": {"value": world_bytes * K / (e2e_total_ms * 1e-3), "unit": "bytes/s",
                     "h2d_bytes_per_step": int(world_h2d), "d2h_bytes_per_step": int(world_d2h),
@@ -611,7 +607,8 @@ def product_arm(args):
         if world > 1:
             line["dict_broadcast_ms"] = bcast_ms
             line["token_gather_ms"] = gather_total_ms / K
-            line["collectives"] = "NCCL (torch.distributed): one broadcast of the packed dictionary, one gather of token records per step"
+            line["collectives"] = ("NCCL: one broadcast of the packed dictionary (torch.distributed), one gather of token records per "
+                                   "step (kp_gather_tokens: the library's grouped ncclSend / ncclRecv of one block per rank)")
             line["strong_scaling"] = strong
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(text, off)

@@ -250,6 +250,24 @@ int kp_shards_times(const kp_shards* g, float ms[4]);
 int kp_shards_copy_to_host(kp_shards* g, void* dst, const void* device_src, uint64_t bytes);
 void kp_shards_destroy(kp_shards* g);
 
+/* ---- token gather across processes (one rank per GPU: torchrun, mpirun, ...) ---------------------------------
+ * The second collective of SURVEY.md 8e for launchers that run one PROCESS per GPU.  Rank 0 obtains an NCCL
+ * unique id (kp_gather_unique_id, 128 bytes) and hands it to the other ranks by whatever channel the launcher
+ * has; every rank then creates its member with the same capacities (sentences / tokens per rank).
+ * kp_gather_tokens takes each rank's device-resident compact result (kp_tokenize_batch_device8) and leaves, on
+ * rank 0, the results of all ranks in device memory in rank order -- global sentence order for contiguous
+ * shards -- with the token offsets rebased; other ranks get an empty *out.  One grouped ncclSend / ncclRecv of a
+ * fixed-capacity block per rank, counts in the block's header, compaction by a kernel on rank 0: no count
+ * exchange and no host round trip before the transfer.  KP_ERR_TOO_LARGE when a shard exceeds the capacity. */
+typedef struct kp_gather kp_gather;
+int kp_gather_unique_id(void* id128);
+int kp_gather_create(int device, int rank, int world, const void* id128, uint64_t cap_sent, uint64_t cap_tok,
+                     kp_gather** out);
+int kp_gather_tokens(kp_gather* g, const kp_result8* mine, kp_result8* out);
+int kp_gather_last_ms(const kp_gather* g, float* ms);     /* device time of the last kp_gather_tokens on this rank */
+int kp_gather_copy_to_host(kp_gather* g, void* dst, const void* device_src, uint64_t bytes);
+void kp_gather_destroy(kp_gather* g);
+
 /* ---- lattice inspection (Lattice{nodes,edges} + viterbi internals) ---------------------------- */
 typedef struct kp_lattice_node {
     int32_t id;          /* node.id(): 0 for BOS/EOS                    src/lattice/node.rs:27-33 */

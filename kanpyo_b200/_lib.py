@@ -95,6 +95,12 @@ SYMBOLS = {
     "kp_shards_times": (C.c_int, [_P, C.POINTER(C.c_float * 4)]),
     "kp_shards_copy_to_host": (C.c_int, [_P, _P, _P, C.c_uint64]),
     "kp_shards_destroy": (None, [_P]),
+    "kp_gather_unique_id": (C.c_int, [_P]),
+    "kp_gather_create": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.c_uint64, C.c_uint64, C.POINTER(_P)]),
+    "kp_gather_tokens": (C.c_int, [_P, C.POINTER(Result8), C.POINTER(Result8)]),
+    "kp_gather_last_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "kp_gather_copy_to_host": (C.c_int, [_P, _P, _P, C.c_uint64]),
+    "kp_gather_destroy": (None, [_P]),
     "kp_last_counters": (C.c_int, [_P, C.POINTER(Counters)]),
     "kp_last_profile": (C.c_int, [_P, C.POINTER(Profile)]),
     "kp_tokenizer_sync": (C.c_int, [_P]),

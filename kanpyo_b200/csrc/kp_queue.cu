@@ -49,6 +49,7 @@ struct NcclApi {
     decltype(&ncclGroupEnd) GroupEnd = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
     decltype(&ncclGetVersion) GetVersion = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
 };
 
 int nccl_load(NcclApi** out) {
@@ -78,6 +79,7 @@ int nccl_load(NcclApi** out) {
         KP_NCCL_SYM(GroupEnd, "ncclGroupEnd")
         KP_NCCL_SYM(GetErrorString, "ncclGetErrorString")
         KP_NCCL_SYM(GetVersion, "ncclGetVersion")
+        KP_NCCL_SYM(AllReduce, "ncclAllReduce")
 #undef KP_NCCL_SYM
         api.handle = h;
     }
@@ -632,6 +634,239 @@ extern "C" int kp_shards_times(const kp_shards* g, float ms[4]) {
 extern "C" int kp_shards_copy_to_host(kp_shards* g, void* dst, const void* device_src, uint64_t bytes) {
     if (!g || (bytes && (!dst || !device_src))) return KP_ERR_ARG;
     KP_CUDA(cudaSetDevice(g->dev[0]->device));
+    if (bytes) KP_CUDA(cudaMemcpy(dst, device_src, bytes, cudaMemcpyDeviceToHost));
+    return KP_OK;
+}
+
+// =====================================================================================================
+// kp_gather: token gather across PROCESSES (one rank per GPU, e.g. under torchrun / mpirun)
+// =====================================================================================================
+// Every rank hands in its device-resident compact result; rank 0 ends up with the results of all ranks in
+// device memory, in rank order (= global sentence order for contiguous shards), offsets rebased.  One grouped
+// ncclSend / ncclRecv of a fixed-capacity block per rank -- no count exchange before the transfer, no host
+// round trip: the counts ride in the block's header and a kernel on rank 0 compacts from them.
+//   block = [n_sent, n_tok : u64 x 2][tok_off u32 x (cap_sent + 1)][eos i32 x cap_sent][tokens 8 B x cap_tok]
+struct kp_gather {
+    int device = 0, rank = 0, world = 1;
+    NcclApi* nccl = nullptr;
+    ncclComm_t comm = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t cap_sent = 0, cap_tok = 0;
+    size_t o_off = 16, o_eos = 0, o_tok = 0, block = 0;
+    void* send = nullptr;            // this rank's block
+    void* recv = nullptr;            // rank 0: world blocks
+    void* g_tok_off = nullptr;       // rank 0: compacted result
+    void* g_tokens = nullptr;
+    void* g_eos = nullptr;
+    uint64_t* d_totals = nullptr;    // rank 0: {sentences, tokens, overflow flag}
+    uint64_t* h_totals = nullptr;    // pinned
+    float last_ms = 0;
+};
+
+extern "C" int kp_gather_unique_id(void* id128) {
+    if (!id128) return KP_ERR_ARG;
+    NcclApi* N = nullptr;
+    int rc = nccl_load(&N);
+    if (rc) return rc;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    auto get = (ncclResult_t(*)(ncclUniqueId*))dlsym(N->handle, "ncclGetUniqueId");
+    if (!get) {
+        kp_set_error("libnccl.so.2 lacks ncclGetUniqueId");
+        return KP_ERR_CUDA;
+    }
+    KP_NCCL(N, get((ncclUniqueId*)id128));
+    return KP_OK;
+}
+
+// rank 0: tokens / offsets / costs of all blocks -> compact arrays.  One block of threads per (rank, slice).
+__global__ void __launch_bounds__(256) kp_gather_compact(const unsigned char* __restrict__ recv, size_t block, uint32_t world,
+                                                         size_t o_off, size_t o_eos, size_t o_tok, uint64_t cap_sent,
+                                                         uint64_t cap_tok, uint32_t* __restrict__ g_off,
+                                                         int32_t* __restrict__ g_eos, uint2* __restrict__ g_tok,
+                                                         uint64_t* __restrict__ totals) {
+    const uint32_t r = blockIdx.y;
+    uint64_t sbase = 0, tbase = 0;
+    bool over = false;
+    for (uint32_t q = 0; q <= r && q < world; q++) {
+        const uint64_t* h = (const uint64_t*)(recv + (size_t)q * block);
+        if (h[0] > cap_sent || h[1] > cap_tok) over = true;
+        if (q < r) {
+            sbase += h[0];
+            tbase += h[1];
+        }
+    }
+    const unsigned char* b = recv + (size_t)r * block;
+    const uint64_t ns = ((const uint64_t*)b)[0], nt = ((const uint64_t*)b)[1];
+    if (over) {                                   // a rank's result did not fit its block: nothing is trusted
+        if (threadIdx.x == 0 && blockIdx.x == 0) totals[2] = 1;
+        return;
+    }
+    const uint32_t* off = (const uint32_t*)(b + o_off);
+    const int32_t* eos = (const int32_t*)(b + o_eos);
+    const uint2* tok = (const uint2*)(b + o_tok);
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < nt; i += stride) g_tok[tbase + i] = tok[i];
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < ns; i += stride) {
+        g_off[sbase + i] = (uint32_t)(tbase + off[i]);
+        g_eos[sbase + i] = eos[i];
+    }
+    if (r == world - 1 && blockIdx.x == 0 && threadIdx.x == 0) {
+        g_off[sbase + ns] = (uint32_t)(tbase + nt);
+        totals[0] = sbase + ns;
+        totals[1] = tbase + nt;
+    }
+}
+
+extern "C" void kp_gather_destroy(kp_gather* g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    if (g->stream) cudaStreamSynchronize(g->stream);
+    if (g->comm && g->nccl) g->nccl->CommDestroy(g->comm);
+    void* bufs[] = {g->send, g->recv, g->g_tok_off, g->g_tokens, g->g_eos, g->d_totals};
+    for (void* p : bufs)
+        if (p) cudaFree(p);
+    if (g->h_totals) cudaFreeHost(g->h_totals);
+    if (g->ev0) cudaEventDestroy(g->ev0);
+    if (g->ev1) cudaEventDestroy(g->ev1);
+    if (g->stream) cudaStreamDestroy(g->stream);
+    delete g;
+}
+
+extern "C" int kp_gather_create(int device, int rank, int world, const void* id128, uint64_t cap_sent, uint64_t cap_tok,
+                                kp_gather** out) {
+    if (!out || !id128 || world < 1 || rank < 0 || rank >= world || cap_sent >= (1ull << 31) || cap_tok >= (1ull << 32))
+        return KP_ERR_ARG;
+    *out = nullptr;
+    NcclApi* N = nullptr;
+    int rc = nccl_load(&N);
+    if (rc) return rc;
+    KP_CUDA(cudaSetDevice(device));
+    kp_gather* g = new kp_gather();
+    g->device = device;
+    g->rank = rank;
+    g->world = world;
+    g->nccl = N;
+    g->cap_sent = cap_sent;
+    g->cap_tok = cap_tok;
+    g->o_eos = g->o_off + 4 * (cap_sent + 1);
+    g->o_tok = (g->o_eos + 4 * cap_sent + 15) & ~size_t(15);
+    g->block = (g->o_tok + 8 * cap_tok + 255) & ~size_t(255);
+    auto init = (ncclResult_t(*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(N->handle, "ncclCommInitRank");
+    cudaError_t e = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&g->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&g->ev1);
+    if (e == cudaSuccess) e = cudaMalloc(&g->send, g->block);
+    if (e == cudaSuccess) e = cudaMemset(g->send, 0, g->block);
+    if (e == cudaSuccess && rank == 0) {
+        e = cudaMalloc(&g->recv, g->block * (size_t)world);
+        if (e == cudaSuccess) e = cudaMalloc(&g->g_tok_off, 4 * ((size_t)cap_sent * world + 1));
+        if (e == cudaSuccess) e = cudaMalloc(&g->g_eos, 4 * ((size_t)cap_sent * world + 1));
+        if (e == cudaSuccess) e = cudaMalloc(&g->g_tokens, 8 * ((size_t)cap_tok * world + 1));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&g->d_totals, 64);
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&g->h_totals, 64, cudaHostAllocDefault);
+    }
+    if (e != cudaSuccess || !init) {
+        kp_set_error("kp_gather_create: %s", init ? cudaGetErrorString(e) : "libnccl.so.2 lacks ncclCommInitRank");
+        cudaGetLastError();
+        kp_gather_destroy(g);
+        return init ? KP_ERR_NOMEM : KP_ERR_CUDA;
+    }
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    ncclResult_t nr = init(&g->comm, world, id, rank);
+    if (nr != ncclSuccess) {
+        kp_set_error("ncclCommInitRank failed: %s", N->GetErrorString(nr));
+        g->comm = nullptr;
+        kp_gather_destroy(g);
+        return KP_ERR_CUDA;
+    }
+    {   // the block layout follows from the capacities: every rank must have passed the same ones
+        int64_t h[4] = {(int64_t)cap_sent, (int64_t)cap_tok, -(int64_t)cap_sent, -(int64_t)cap_tok};
+        int64_t* dv = nullptr;
+        cudaError_t e2 = cudaMalloc((void**)&dv, sizeof(h));
+        if (e2 == cudaSuccess) e2 = cudaMemcpy(dv, h, sizeof(h), cudaMemcpyHostToDevice);
+        ncclResult_t r2 = ncclSuccess;
+        if (e2 == cudaSuccess) r2 = N->AllReduce(dv, dv, 4, ncclInt64, ncclMax, g->comm, g->stream);
+        if (e2 == cudaSuccess && r2 == ncclSuccess) e2 = cudaStreamSynchronize(g->stream);
+        if (e2 == cudaSuccess && r2 == ncclSuccess) e2 = cudaMemcpy(h, dv, sizeof(h), cudaMemcpyDeviceToHost);
+        if (dv) cudaFree(dv);
+        if (e2 != cudaSuccess || r2 != ncclSuccess || h[0] != -h[2] || h[1] != -h[3]) {
+            if (e2 != cudaSuccess || r2 != ncclSuccess) kp_set_error("kp_gather_create: capacity check failed");
+            else kp_set_error("kp_gather_create: ranks disagree on the capacities (%lld..%lld sentences, %lld..%lld tokens)",
+                              (long long)-h[2], (long long)h[0], (long long)-h[3], (long long)h[1]);
+            kp_gather_destroy(g);
+            return e2 != cudaSuccess || r2 != ncclSuccess ? KP_ERR_CUDA : KP_ERR_ARG;
+        }
+    }
+    *out = g;
+    return KP_OK;
+}
+
+extern "C" int kp_gather_tokens(kp_gather* g, const kp_result8* mine, kp_result8* out) {
+    if (!g || !mine || !out) return KP_ERR_ARG;
+    if (mine->n_sent > g->cap_sent || mine->n_tokens > g->cap_tok) {
+        kp_set_error("shard (%llu sentences, %llu tokens) exceeds the gather capacity (%llu, %llu)",
+                     (unsigned long long)mine->n_sent, (unsigned long long)mine->n_tokens, (unsigned long long)g->cap_sent,
+                     (unsigned long long)g->cap_tok);
+        return KP_ERR_TOO_LARGE;
+    }
+    KP_CUDA(cudaSetDevice(g->device));
+    cudaStream_t st = g->stream;
+    NcclApi* N = g->nccl;
+    char* s = (char*)g->send;
+    const uint64_t hdr[2] = {mine->n_sent, mine->n_tokens};
+    KP_CUDA(cudaEventRecord(g->ev0, st));
+    // this rank's block: header, offsets, costs, token records (the caller's result is complete: its call synchronised)
+    KP_CUDA(cudaMemcpyAsync(s, hdr, 16, cudaMemcpyHostToDevice, st));
+    KP_CUDA(cudaMemcpyAsync(s + g->o_off, mine->tok_off, 4 * (mine->n_sent + 1), cudaMemcpyDeviceToDevice, st));
+    if (mine->n_sent) KP_CUDA(cudaMemcpyAsync(s + g->o_eos, mine->eos_cost, 4 * mine->n_sent, cudaMemcpyDeviceToDevice, st));
+    if (mine->n_tokens) KP_CUDA(cudaMemcpyAsync(s + g->o_tok, mine->tokens, 8 * mine->n_tokens, cudaMemcpyDeviceToDevice, st));
+    if (g->rank == 0) {
+        KP_CUDA(cudaMemcpyAsync(g->recv, s, g->block, cudaMemcpyDeviceToDevice, st));
+        if (g->world > 1) {
+            KP_NCCL(N, N->GroupStart());
+            for (int r = 1; r < g->world; r++)
+                KP_NCCL(N, N->Recv((char*)g->recv + (size_t)r * g->block, g->block, ncclChar, r, g->comm, st));
+            KP_NCCL(N, N->GroupEnd());
+        }
+        KP_CUDA(cudaMemsetAsync(g->d_totals, 0, 64, st));
+        dim3 grid(64, (unsigned)g->world);
+        kp_gather_compact<<<grid, 256, 0, st>>>((const unsigned char*)g->recv, g->block, (uint32_t)g->world, g->o_off, g->o_eos,
+                                                g->o_tok, g->cap_sent, g->cap_tok, (uint32_t*)g->g_tok_off, (int32_t*)g->g_eos,
+                                                (uint2*)g->g_tokens, g->d_totals);
+        KP_CUDA(cudaGetLastError());
+        KP_CUDA(cudaMemcpyAsync(g->h_totals, g->d_totals, 24, cudaMemcpyDeviceToHost, st));
+    } else {
+        KP_NCCL(N, N->Send(s, g->block, ncclChar, 0, g->comm, st));
+    }
+    KP_CUDA(cudaEventRecord(g->ev1, st));
+    KP_CUDA(cudaEventSynchronize(g->ev1));
+    cudaEventElapsedTime(&g->last_ms, g->ev0, g->ev1);
+    memset(out, 0, sizeof(*out));
+    if (g->rank == 0) {
+        if (g->h_totals[2]) {
+            kp_set_error("a rank's result exceeded the gather capacity");
+            return KP_ERR_TOO_LARGE;
+        }
+        out->n_sent = g->h_totals[0];
+        out->n_tokens = g->h_totals[1];
+        out->tok_off = (const uint32_t*)g->g_tok_off;
+        out->tokens = (const kp_token8*)g->g_tokens;
+        out->eos_cost = (const int32_t*)g->g_eos;
+    }
+    return KP_OK;
+}
+
+extern "C" int kp_gather_last_ms(const kp_gather* g, float* ms) {
+    if (!g || !ms) return KP_ERR_ARG;
+    *ms = g->last_ms;
+    return KP_OK;
+}
+
+extern "C" int kp_gather_copy_to_host(kp_gather* g, void* dst, const void* device_src, uint64_t bytes) {
+    if (!g || (bytes && (!dst || !device_src))) return KP_ERR_ARG;
+    KP_CUDA(cudaSetDevice(g->device));
     if (bytes) KP_CUDA(cudaMemcpy(dst, device_src, bytes, cudaMemcpyDeviceToHost));
     return KP_OK;
 }

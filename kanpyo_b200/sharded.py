@@ -6,6 +6,8 @@ the algorithm.  Exactly two collectives exist, both outside the k
   * `broadcast_dict_blob` — ONE broadcast of the packed dictionary blob (17.5 MB for IPADIC) from the
     rank that built it; every rank stages its handle from the blob in HBM
     (`kp_dict_create_from_device_blob`: checksum-validated, copied into memory the handle owns).
+  * `NcclGather.gather`   — the same gather behind the C ABI (`kp_gather_*`): the library's own grouped
+    ncclSend / ncclRecv + a compaction kernel on rank 0; what bench.py times.
   * `TokenGather.gather`  — tokens of all shards to one rank, in global sentence order: ONE `gather`
     collective over preallocated fixed-capacity buffers (counts ride in a 16-byte header; no count
     exchange, no allocation, one host sync on the receiving rank).
@@ -115,6 +117,72 @@ class TokenGather:
         g_eos = torch.cat([eoss[k, :ns[k]] for k in range(self.world)])
         g_tok = torch.cat([r[k, self.o_tok:self.o_tok + 8 * nt[k]] for k in range(self.world)])
         return g_off, g_tok, g_eos
+
+
+class NcclGather:
+    """kp_gather_*: the token gather behind the C ABI for one-process-per-GPU launchers.  The NCCL unique id
+    travels from rank 0 through `torch.distributed` (any channel would do); from then on the transfer is the
+    library's own grouped ncclSend / ncclRecv of one fixed-capacity block per rank plus a compaction kernel on
+    rank 0 -- no count exchange, no host round trip, nothing allocated per call."""
+
+    def __init__(self, device: int, cap_sent: int, cap_tok: int, group=None):
+        import ctypes as C
+        from . import _lib
+        self._L = _lib.load()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = device
+        uid = np.zeros(128, np.uint8)
+        if self.rank == 0:
+            _lib.check(self._L.kp_gather_unique_id(uid.ctypes.data_as(C.c_void_p)))
+        backend = dist.get_backend(group)
+        t = torch.from_numpy(uid)
+        if backend == "nccl":
+            t = t.to("cuda:%d" % device)
+        dist.broadcast(t, 0, group=group)
+        uid = t.cpu().numpy()
+        self._h = C.c_void_p()
+        _lib.check(self._L.kp_gather_create(device, self.rank, self.world, uid.ctypes.data_as(C.c_void_p), int(cap_sent),
+                                            int(cap_tok), C.byref(self._h)))
+
+    def gather(self, mine):
+        """mine: _lib.Result8 with DEVICE pointers (Tokenizer.tokenize_batch_device8).  -> Result8 on rank 0 (device
+        pointers owned by the gather, valid until its next call), an empty Result8 elsewhere."""
+        import ctypes as C
+        from . import _lib
+        out = _lib.Result8()
+        _lib.check(self._L.kp_gather_tokens(self._h, C.byref(mine), C.byref(out)))
+        return out
+
+    def last_ms(self) -> float:
+        import ctypes as C
+        from . import _lib
+        ms = C.c_float()
+        _lib.check(self._L.kp_gather_last_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def to_host(self, r):
+        """Gathered device result -> (tok_off u32, tokens TOKEN8_DTYPE, eos i32) numpy copies."""
+        import ctypes as C
+        from . import _lib
+        n, nt = int(r.n_sent), int(r.n_tokens)
+        tok_off = np.empty(n + 1, np.uint32)
+        tokens = np.empty(nt, TOKEN8_DTYPE)
+        eos = np.empty(n, np.int32)
+        for dst, src in ((tok_off, r.tok_off), (tokens, r.tokens), (eos, r.eos_cost)):
+            if dst.nbytes:
+                _lib.check(self._L.kp_gather_copy_to_host(self._h, dst.ctypes.data_as(C.c_void_p), src, dst.nbytes))
+        return tok_off, tokens, eos
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.kp_gather_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def to_batch_result(tok_off: torch.Tensor, tokens8: torch.Tensor, eos_cost: torch.Tensor, offsets) -> BatchResult:

@@ -326,6 +326,7 @@ def test_sharded_tokenizer_single_rank(gpu_ipadic, oracle_tok, vocab):
     world-size-1 path.  The caller's Dict (and the session tokenizer built on it) stay usable."""
     import torch
     import torch.distributed as dist
+    import kanpyo_b200
     from kanpyo_b200 import corpus, sharded
     if not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -338,6 +339,22 @@ def test_sharded_tokenizer_single_rank(gpu_ipadic, oracle_tok, vocab):
         o_off, o_tok, o_cost, _ = oracle_tok.tokenize_batch(text, off)
         assert_batch_equal(res, o_off, o_tok, o_cost)
         assert st.dict is not gpu_ipadic
+        # kp_gather_* (the gather behind the C ABI) with a world of one: block assembly + compaction kernel
+        from kanpyo_b200.tokenizer import result8_to_batch
+        d_text = torch.from_numpy(text.copy()).cuda()
+        d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+        torch.cuda.synchronize()
+        r = st.tokenizer.tokenize_batch_device8(d_text.data_ptr(), d_off.data_ptr(), len(off) - 1, 0, int(text.size))
+        ng = sharded.NcclGather(0, len(off) - 1, int(r.n_tokens) + 5)
+        g = ng.gather(r)
+        assert int(g.n_sent) == len(off) - 1 and ng.last_ms() > 0
+        assert_batch_equal(result8_to_batch(ng.to_host(g), off), o_off, o_tok, o_cost)
+        small = sharded.NcclGather(0, len(off) - 1, 10)
+        with pytest.raises(kanpyo_b200.KanpyoB200Error) as e:      # a shard beyond the capacity is refused, never truncated
+            small.gather(r)
+        assert e.value.status == -6
+        ng.close()
+        small.close()
     finally:
         dist.destroy_process_group()
 

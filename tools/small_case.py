@@ -21,10 +21,23 @@ for s in ["ã™ã‚‚ã‚‚ã‚‚ã‚‚ã‚‚ã‚‚ã‚‚ã‚‚ã®ã†ã¡", "", "Tã‚·ãƒ£ãƒ„ã‚’3æšè²·ã£ã
     print("  oracle:", orc.tokenize(s)[1], [(t[0], t[5]) for t in orc.tokenize(s)[0]], flush=True)
 v = corpus.Vocabulary(od.keywords, od.morphs)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-text, off = corpus.synth_corpus(v, n, "cfg2")
-res = tk.tokenize_batch_bytes(text, off)
-o_off, o_tok, o_cost, ctr = orc.tokenize_batch(text, off, threads=4)
-print("gpu tokens", len(res.tokens), "oracle tokens", len(o_tok), "counters", tk.counters(), ctr, flush=True)
-print("profile", tk.profile(), flush=True)
-assert_batch_equal(res, o_off, o_tok, o_cost)
-print("PARITY OK on", n, "sentences")
+edge = ["", "ã‚", "ãƒ¼" * 300, "a" * 500, "ã‚¢" * 1030, "\x00ã‚\x00ã„", "ğ ®·é‡å®¶ã§ğ©¸½ã‚’é£Ÿã¹ãŸ", "1" * 60 + "çŠ¬" + "ã‚¢" * 40 + "abc" * 30]
+for kind, m in (("cfg2", n), ("cfg3", n + 70)):          # n <= 64: the one-round-trip path; above: classify + class kernels
+    text, off = corpus.synth_corpus(v, m, kind)
+    for path in ("fused", "pipeline"):
+        tk.set_path(path)
+        res = tk.tokenize_batch_bytes(text, off)
+        o_off, o_tok, o_cost, ctr = orc.tokenize_batch(text, off, threads=4)
+        print(kind, path, "gpu tokens", len(res.tokens), "oracle tokens", len(o_tok), "counters", tk.counters(), ctr, flush=True)
+        print("profile", tk.profile(), flush=True)
+        assert_batch_equal(res, o_off, o_tok, o_cost)
+for path in ("fused", "pipeline"):
+    tk.set_path(path)
+    blobs = [e.encode("utf-8") for e in edge]
+    eoff = np.zeros(len(blobs) + 1, np.uint64)
+    eoff[1:] = np.cumsum([len(b) for b in blobs])
+    etext = np.frombuffer(b"".join(blobs), np.uint8)
+    res = tk.tokenize_batch_bytes(etext, eoff)
+    o_off, o_tok, o_cost, _ = orc.tokenize_batch(etext, eoff)
+    assert_batch_equal(res, o_off, o_tok, o_cost)
+print("PARITY OK on", n, "sentences, both paths")

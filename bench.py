@@ -639,7 +639,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the benched batch (debug)")
     ap.add_argument("--path", default="auto", choices=["auto", "pipeline", "fused"])
-    ap.add_argument("--queue-depth", type=int, default=2)
+    ap.add_argument("--queue-depth", type=int, default=3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -23,7 +23,10 @@ from __future__ import annotations
 
 import ctypes as C
 import hashlib
+import csv
+import io
 import os
+import re
 import tarfile
 
 import numpy as np
@@ -102,48 +105,47 @@ class _Source:
         return sorted(n for n in self.files if n.endswith(".csv"))   # glob *.csv (builder.rs:27-44)
 
 
-def _split_csv_line(line: str):
-    """One record of the `csv` crate's default dialect: comma separated, '"' quoting with '""' escape."""
-    if '"' not in line:
-        return line.split(",")
-    out, cur, i, n, quoted = [], [], 0, len(line), False
-    while i < n:
-        ch = line[i]
-        if quoted:
-            if ch == '"':
-                if i + 1 < n and line[i + 1] == '"':
-                    cur.append('"')
-                    i += 1
-                else:
-                    quoted = False
-            else:
-                cur.append(ch)
-        elif ch == '"' and not cur:
-            quoted = True
-        elif ch == ",":
-            out.append("".join(cur))
-            cur = []
-        else:
-            cur.append(ch)
-        i += 1
-    out.append("".join(cur))
-    return out
+_USIZE = re.compile(r"^\+?[0-9]+$")      # what `str::parse::<usize>` accepts (a leading '+' is legal, '-', blanks, '_' are not)
+_I64 = re.compile(r"^[+-]?[0-9]+$")       # `str::parse::<i64>`
+
+
+def _parse_usize(tok: str) -> int:
+    if not _USIZE.match(tok) or int(tok) >= 1 << 64:
+        raise ValueError(tok)
+    return int(tok)
+
+
+def _parse_i64(tok: str) -> int:
+    if not _I64.match(tok) or not -(1 << 63) <= int(tok) < 1 << 63:
+        raise ValueError(tok)
+    return int(tok)
 
 
 def _read_records(text: str, what: str):
-    """parse_csv (record.rs:21-42): no header row; surface, left_id, right_id, cost, then user data."""
-    rows = []
-    for ln, raw in enumerate(text.split("\n"), 1):
-        line = raw[:-1] if raw.endswith("\r") else raw
-        if not line:
-            continue
-        f = _split_csv_line(line)
-        if len(f) < 4:
-            raise BuilderError("%s:%d: expected at least 4 fields" % (what, ln))
-        try:
-            rows.append((f[0].encode("utf-8"), int(f[1]), int(f[2]), int(f[3]), tuple(x.encode("utf-8") for x in f[4:])))
-        except ValueError:
-            raise BuilderError("%s:%d: left_id / right_id / cost must be integers" % (what, ln)) from None
+    """parse_csv (record.rs:21-42) with the `csv` crate's default reader: no header row, '"' quoting with '""'
+    escapes (a quoted field may hold commas and line breaks), empty lines skipped, and every record must have
+    as many fields as the first one; surface, left_id (usize), right_id (usize), cost (i64), then user data."""
+    rows, width = [], None
+    reader = csv.reader(io.StringIO(text, newline=""), strict=True)
+    try:
+        for f in reader:
+            if not f:
+                continue
+            if width is None:
+                width = len(f)
+            elif len(f) != width:
+                raise BuilderError("%s:%d: found record with %d fields, but the previous record has %d fields"
+                                   % (what, reader.line_num, len(f), width))
+            if len(f) < 4:
+                raise BuilderError("%s:%d: expected at least 4 fields" % (what, reader.line_num))
+            try:
+                rows.append((f[0].encode("utf-8"), _parse_usize(f[1]), _parse_usize(f[2]), _parse_i64(f[3]),
+                             tuple(x.encode("utf-8") for x in f[4:])))
+            except ValueError:
+                raise BuilderError("%s:%d: left_id / right_id must parse as usize and cost as i64 (record.rs:35-37)"
+                                   % (what, reader.line_num)) from None
+    except csv.Error as e:
+        raise BuilderError("%s:%d: malformed CSV: %s" % (what, reader.line_num, e)) from None
     return rows
 
 

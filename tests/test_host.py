@@ -474,3 +474,20 @@ def test_blob_is_refused_unless_it_is_what_pack_wrote(oracle_mod):
     assert status(hdr.view(np.uint8)) == -7
     ver = blob.copy(); ver[8] = 1                 # layout version 1 (round 1) is not accepted
     assert status(ver) == -7
+
+
+def test_builder_csv_is_as_strict_as_the_reference():
+    """parse_csv (kanpyo-dict/src/builder/record.rs:21-42) reads with the `csv` crate and `str::parse`: quoted fields
+    may hold commas and line breaks, every record has the first record's field count, ids parse as usize and the cost
+    as i64 (a leading '+' is legal; '-' on an id, blanks, '_' are not).  What the reference refuses is refused here."""
+    from kanpyo_b200.builder import BuilderError, _read_records
+    rows = _read_records('東京,1,2,300,名詞,"a,b"\n"京\n都",+3,4,-5,名詞,"say ""hi"""\n\n', "t.csv")
+    assert rows == [("東京".encode(), 1, 2, 300, ("名詞".encode(), b"a,b")),
+                    ("京\n都".encode(), 3, 4, -5, ("名詞".encode(), b'say "hi"'))]
+    for bad in ["a,1,2,3,x\nb,1,2,3\n",          # differing field counts
+                "a,-1,2,3\n", "a,1,-2,3\n",      # negative ids
+                "a,1_000,2,3\n", "a, 1,2,3\n", "a,1,2,3.0\n", "a,1,2,\n", "a,0x10,2,3\n",
+                "a,1,2\n",                        # fewer than four fields
+                "a,1,2,99999999999999999999\n"]:  # cost beyond i64
+        with pytest.raises(BuilderError):
+            _read_records(bad, "t.csv")

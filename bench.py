@@ -137,6 +137,33 @@ def host_info():
     return len(os.sched_getaffinity(0)), model
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """What `numactl --cpunodebind --membind` does for a one-process-per-GPU launch: run this rank (and first-touch its
+    pinned buffers) on the NUMA node its GPU hangs off, so the H2D / D2H of eight ranks do not all cross the socket
+    link.  Topology from NVML + sysfs; any failure leaves the affinity untouched.  Returns a description or None."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(gpu_index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:            # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) < 2:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return "numa node %d (%d cpus)" % (node, len(cpus))
+    except Exception:   # noqa: BLE001
+        return None
+
+
 def load_dict_and_corpus(kind, n_sent, seed_offset, rank=0, world=1, barrier=None):
     """The product's dictionary and the synthetic batch of rank `seed_offset` (seed = corpus.SEED + rank)."""
     from kanpyo_b200 import builder, corpus
@@ -294,6 +321,7 @@ def product_arm(args):
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda:%d" % local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 and not args.no_numa else None
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=4))
@@ -605,6 +633,7 @@ def product_arm(args):
             "clocks": clocks,
         }
         if world > 1:
+            line["config"]["host_affinity"] = ("each rank bound to its GPU's " + numa) if numa else "not bound"
             line["dict_broadcast_ms"] = bcast_ms
             line["token_gather_ms"] = gather_total_ms / K
             line["collectives"] = ("NCCL: one broadcast of the packed dictionary (torch.distributed), one gather of token records per "
@@ -640,6 +669,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the benched batch (debug)")
     ap.add_argument("--path", default="auto", choices=["auto", "pipeline", "fused"])
     ap.add_argument("--queue-depth", type=int, default=3)
+    ap.add_argument("--no-numa", action="store_true", help="N > 1: do not bind each rank to its GPU's NUMA node")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

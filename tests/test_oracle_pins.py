@@ -190,3 +190,33 @@ def test_golden_cfg2_slice(oracle_tok, vocab):
     tok_off2, tokens2, cost2, ctr2 = oracle_tok.tokenize_batch(text, off, threads=4)
     assert np.array_equal(tok_off, tok_off2) and np.array_equal(tokens, tokens2) and np.array_equal(cost, cost2)
     assert ctr == ctr2
+
+
+def test_token_ids_follow_the_whatwg_euc_jp_decoder():
+    """Token ids are ranks in the byte-wise sort of the DECODED surfaces (builder.rs:46-57, record.rs derived Ord), so
+    the decoder matters.  The reference decodes with `encoding_rs::EUC_JP` (record.rs:23), which is the WHATWG decoder:
+    its jis0208 index is the Windows-31J table, not the JIS X 0208 table behind Python's `euc_jp`.  Five IPADIC records
+    (Symbol.csv) move from below every kana surface to above it under the WHATWG table -- '£' (A1F2), '−' (A1DD),
+    '−−', and the two '〜' (A1C1) rows -- which lowers the id of every surface in between by 5: すもも is 36164 here,
+    36169 under Python's codec (the figure SURVEY.md section 8c derived with a throwaway script).  Both decoders are
+    pinned here on the rank of すもも and on the records that differ."""
+    import tarfile
+    from oracle import eucjp, oracle
+    surfaces_jis, surfaces_whatwg = [], []
+    with tarfile.open(oracle.IPADIC_TARBALL, "r:*") as tar:
+        for m in tar.getmembers():
+            if not m.name.endswith(".csv"):
+                continue
+            raw = tar.extractfile(m).read()
+            for a, b in ((surfaces_jis, raw.decode("euc_jp")), (surfaces_whatwg, eucjp.decode(raw))):
+                a.extend(line.split(",", 1)[0].encode("utf-8") for line in b.split("\n") if line)
+    assert len(surfaces_jis) == len(surfaces_whatwg) == 392126
+    moved = sorted((a.decode(), b.decode()) for a, b in zip(surfaces_jis, surfaces_whatwg) if a != b)
+    assert len(moved) == 21                                       # 21 records hold one of the four re-mapped characters
+    target = "すもも".encode("utf-8")
+    rank = lambda surfaces: sum(s < target for s in surfaces) + 1   # noqa: E731  (1-based id of the first すもも record)
+    assert rank(surfaces_jis) == 36169 and rank(surfaces_whatwg) == 36164
+    crossing = sorted(a for a, b in moved if a.encode() < target <= b.encode())
+    assert crossing == sorted(["£", "−", "−−", "〜", "〜"])
+    od = oracle.load_ipadic()
+    assert od.keywords[36164 - 1] == target and od.keywords[36164 - 2] != target

@@ -5,6 +5,7 @@ use kanpyo_dict::{dict::Dict, morph::Morph};
 
 use crate::ffi;
 use crate::lattice::node::{Node, Word};
+use crate::tokenizer::device_of;
 
 pub mod node; // unchanged: src/lattice/node.rs
 
@@ -16,7 +17,15 @@ pub struct Lattice<'a> {
 }
 
 impl<'a> Lattice<'a> {
-    /// `handle` is the `kp_tokenizer*` owned by the `Tokenizer` (one per thread).
+    /// The reference's signature (src/lattice.rs:101), so `src/bin/kanpyo.rs:146` and `src/graphviz.rs` compile
+    /// unchanged: the device state of `dict` is found (or created) through the registry in `tokenizer.rs`, and a
+    /// tokenizer handle is borrowed from its pool for the duration of the call.
+    pub fn build(dict: &'a Dict, input: &str) -> Self {
+        let device = device_of(dict);
+        device.with_handle(|handle| Self::build_with(handle, dict, input))
+    }
+
+    /// `handle`: a `kp_tokenizer*` nobody else uses during the call.
     pub fn build_with(handle: *mut ffi::kp_tokenizer, dict: &'a Dict, input: &str) -> Self {
         let mut la = std::mem::MaybeUninit::<ffi::kp_lattice>::uninit();
         let la = unsafe {
@@ -24,6 +33,7 @@ impl<'a> Lattice<'a> {
             assert_eq!(rc, ffi::KP_OK, "kp_lattice_dump failed");
             la.assume_init()
         };
+        // the node table is copied out below, before the handle returns to the pool
         let raw = unsafe { std::slice::from_raw_parts(la.nodes, la.n_nodes as usize) };
         let n_chars = input.chars().count();
         let byte_of_char: Vec<usize> =

@@ -337,8 +337,11 @@ int chunk_compute(kp_tokenizer* t, kp_chunk& c, uint64_t* n_tokens, StageTimes* 
     // which device path: the fused per-sentence kernel keeps a sentence on chip but holds few sentences per SM, so
     // it wins where the batch is too small to fill the pipeline's kernels (and for single sentences, where the
     // pipeline's dozen launches and three round trips dominate); KP_PATH_FUSED / _PIPELINE force either one
+    // (a batch whose MEAN sentence is longer than the largest size class -- long-line input -- is the pipeline's anyway)
+    const uint64_t largest = t->fclasses.n ? t->fclasses.c[t->fclasses.n - 1].max_bytes : 0;
     const bool fused = t->fused_ok && !t->count_work && S > 0 &&
-                       (t->path_mode == KP_PATH_FUSED || (t->path_mode == KP_PATH_AUTO && S <= t->fused_max_batch));
+                       (t->path_mode == KP_PATH_FUSED ||
+                        (t->path_mode == KP_PATH_AUTO && S <= t->fused_max_batch && (uint64_t)c.B <= largest * S));
     if (fused) {
         // fused per-sentence kernel first; the pipeline then takes the sentences it left (c.sel)
         uint32_t left = 0;

@@ -345,7 +345,8 @@ def product_arm(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         blob = d.pack() if rank == 0 else None
         warm = torch.zeros(1, device=dev)
-        dist.all_reduce(warm)              # NCCL communicator setup is not part of the broadcast
+        dist.all_reduce(warm)              # NCCL communicator / channel setup is not part of the broadcast
+        dist.broadcast(torch.zeros(1 << 20, dtype=torch.uint8, device=dev), 0)
         barrier()
         e0.record()
         blob_t = sharded.broadcast_dict_blob(blob, 0, dev)

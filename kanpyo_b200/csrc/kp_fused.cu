@@ -15,9 +15,15 @@
 //   tokens    staged at the sentence's slot of the staging area               tokenizer.rs:22-43
 //
 // Only the dictionary (L2-resident) and the sentence's own bytes are read from global memory; only the
-// tokens, the token count and dp[EOS] are written.  Sentences that do not fit the launch's capacities
-// (chars, nodes, hits) are appended to a list and taken by the pipeline afterwards: results are
-// identical either way (tests/test_gpu_parity.py runs both).
+// tokens, the token count and dp[EOS] are written.  Sentences come in size classes (by bytes), each
+// launch with its own capacities; a sentence that does not fit its class (chars, nodes, hits) is appended
+// to the largest class's list, which runs last, and what does not fit that one is taken by the pipeline
+// afterwards: results are identical either way (tests/test_gpu_parity.py runs both).
+//
+// Where it is used: one line per call and small batches (one launch, one host round trip), where the
+// pipeline's dozen launches dominate.  For tens of thousands of sentences the pipeline is ~2x faster: it
+// amortises a sweep step over four sentences per warp and keeps 160 sentences in flight per SM where
+// shared memory holds 8-17 here (profiles/r02_fused_kernel.md has the ncu evidence).
 //
 // Exactness notes
 //   * Unknown nodes are not materialised.  Every start inside a same-class run emits the class's unknown
@@ -27,8 +33,10 @@
 //   * The reference keeps the FIRST predecessor attaining the minimum in `edges[p]` order, which is
 //     insertion order: ascending start, known before unknown, ascending id (two nodes of one bucket with
 //     the same start have the same length, hence come from the same trie hit or the same class).  Bucket
-//     slots are handed out by atomics here, so the back-trace compares the key (start, kind, id) instead
-//     of the slot index: same winner.
+//     slots are handed out by atomics here, so the back-trace compares the key (start, slot) instead of
+//     the slot alone: a hit's duplicates take consecutive slots in id order, the unknown ids' shared slots
+//     sit behind the known ones in id order, and a shared slot remembers its first minimal start --
+//     ascending (start, slot) is the reference's order among the entries that can tie.
 //   * dp arithmetic is the reference's: dp = min(min_j(dp_j + conn) + cost, INF), BOS = 0, a node without
 //     predecessor (or with dead ones only) keeps INF and cuts the path.
 #include <limits.h>

@@ -9,6 +9,8 @@
 //   Tokenizer::tokenize(&self, &str)     src/tokenizer.rs:16-45    Tokenizer::tokenize(std::string_view)
 //   kanpyo::lattice::node::Node          src/lattice/node.rs:16-52 kanpyo::LatticeNode
 //   Lattice::build + Lattice::viterbi    src/lattice.rs:101,116    Tokenizer::lattice(std::string_view)
+//   (new) batches in flight                                        kanpyo::Queue   (kp_queue_*: copies hidden behind kernels)
+//   (new) every GPU of the box, one process                        kanpyo::Shards  (kp_shards_*: NCCL broadcast, sentence shards)
 //
 // Error behaviour: the reference's `tokenize` is infallible by signature and panics on an index out
 // of range; here a non-zero C-ABI status (no GPU, invalid UTF-8, out of memory) throws kanpyo::Error,
@@ -20,8 +22,10 @@
 #ifndef KANPYO_B200_HPP
 #define KANPYO_B200_HPP
 
+#include <climits>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -137,6 +141,44 @@ class Tokenizer {
         return out;
     }
 
+    // The same through the compact transfer records (kp_token8: half the device-to-host bytes); position / start
+    // are rebuilt on the host by kp_expand_tokens8.
+    std::vector<std::vector<Token>> tokenize_batch_compact(const std::vector<std::string_view>& inputs) const {
+        std::string text;
+        std::vector<uint64_t> off;
+        pack(inputs, &text, &off);
+        kp_result8 r;
+        check(kp_tokenize_batch8(h_.get(), reinterpret_cast<const uint8_t*>(text.data()), off.data(), inputs.size(), &r));
+        return materialize8(inputs, r, off);
+    }
+
+    // KP_PATH_AUTO / KP_PATH_PIPELINE / KP_PATH_FUSED: which device path serves the calls (identical results).
+    void set_path(int path) { check(kp_tokenizer_set_path(h_.get(), path)); }
+
+    static void pack(const std::vector<std::string_view>& inputs, std::string* text, std::vector<uint64_t>* off) {
+        off->assign(inputs.size() + 1, 0);
+        for (size_t i = 0; i < inputs.size(); i++) {
+            text->append(inputs[i]);
+            (*off)[i + 1] = text->size();
+        }
+    }
+
+    static std::vector<std::vector<Token>> materialize8(const std::vector<std::string_view>& inputs, const kp_result8& r,
+                                                        const std::vector<uint64_t>& off) {
+        std::vector<kp_token> full(r.n_tokens);
+        check(kp_expand_tokens8(&r, off.data(), full.data()));
+        std::vector<uint64_t> tok_off(r.tok_off, r.tok_off + r.n_sent + 1);
+        kp_result wide;
+        wide.n_sent = r.n_sent;
+        wide.n_tokens = r.n_tokens;
+        wide.tok_off = tok_off.data();
+        wide.tokens = full.data();
+        wide.eos_cost = r.eos_cost;
+        std::vector<std::vector<Token>> out(inputs.size());
+        for (size_t i = 0; i < inputs.size(); i++) out[i] = materialize(inputs[i], wide, i);
+        return out;
+    }
+
     // dp[EOS] of the last tokenize() call's sentence `s` is not kept here; use tokenize_with_cost.
     std::pair<std::vector<Token>, int32_t> tokenize_with_cost(std::string_view input) const {
         kp_result r;
@@ -162,7 +204,6 @@ class Tokenizer {
     kp_tokenizer* handle() const { return h_.get(); }
     const Dict& dict() const { return dict_; }                          // `pub dict: Dict`, src/tokenizer.rs:8
 
-  private:
     static std::vector<Token> materialize(std::string_view input, const kp_result& r, uint64_t s) {
         std::vector<Token> out;
         const uint64_t a = r.tok_off[s], b = r.tok_off[s + 1];
@@ -182,8 +223,74 @@ class Tokenizer {
         return out;
     }
 
+  private:
     Dict dict_;
     std::shared_ptr<kp_tokenizer> h_;
+};
+
+// Successive batches in flight on `depth` tokenizer contexts (kp_queue_*): submit() returns at once, wait() blocks
+// for that batch's tokens.  The inputs are copied into the ticket, so the caller's strings may go away.
+class Queue {
+  public:
+    explicit Queue(const Dict& dict, uint32_t depth = 3) : dict_(dict), depth_(depth), slots_(depth) {
+        kp_queue* q = nullptr;
+        check(kp_queue_create(dict_.handle(), depth, &q));
+        h_.reset(q, kp_queue_destroy);
+    }
+    uint64_t submit(const std::vector<std::string_view>& inputs) {
+        Slot& s = slots_[next_ % depth_];
+        s.inputs.assign(inputs.begin(), inputs.end());
+        s.text.clear();
+        std::vector<std::string_view> views(s.inputs.begin(), s.inputs.end());
+        Tokenizer::pack(views, &s.text, &s.off);
+        uint64_t ticket = 0;
+        check(kp_queue_submit(h_.get(), reinterpret_cast<const uint8_t*>(s.text.data()), s.off.data(), inputs.size(), &ticket));
+        next_ = ticket + 1;
+        return ticket;
+    }
+    std::vector<std::vector<Token>> wait(uint64_t ticket) {
+        kp_result8 r;
+        check(kp_queue_wait(h_.get(), ticket, &r));
+        const Slot& s = slots_[ticket % depth_];
+        std::vector<std::string_view> views(s.inputs.begin(), s.inputs.end());
+        return Tokenizer::materialize8(views, r, s.off);
+    }
+
+  private:
+    struct Slot {
+        std::vector<std::string> inputs;
+        std::string text;
+        std::vector<uint64_t> off;
+    };
+    Dict dict_;
+    uint32_t depth_;
+    uint64_t next_ = 0;
+    std::vector<Slot> slots_;
+    std::shared_ptr<kp_queue> h_;
+};
+
+// Every GPU of the box from one process (kp_shards_*): the dictionary is packed once and broadcast with NCCL, a
+// batch is split into byte-balanced contiguous sentence ranges, one per GPU.
+class Shards {
+  public:
+    explicit Shards(const kp_dict_arrays& arrays, const std::vector<int>& devices = {}) {
+        int n = (int)devices.size();
+        if (n == 0) check(kp_device_count(&n));
+        kp_shards* g = nullptr;
+        check(kp_shards_create(&arrays, devices.empty() ? nullptr : devices.data(), n, &g));
+        h_.reset(g, kp_shards_destroy);
+    }
+    std::vector<std::vector<Token>> tokenize_batch(const std::vector<std::string_view>& inputs) const {
+        std::string text;
+        std::vector<uint64_t> off;
+        Tokenizer::pack(inputs, &text, &off);
+        kp_result8 r;
+        check(kp_shards_tokenize(h_.get(), reinterpret_cast<const uint8_t*>(text.data()), off.data(), inputs.size(), &r));
+        return Tokenizer::materialize8(inputs, r, off);
+    }
+
+  private:
+    std::shared_ptr<kp_shards> h_;
 };
 
 }  // namespace kanpyo

@@ -29,8 +29,15 @@ static size_t chars(const std::string& s) {
 }
 
 // create_test_dict(), src/tests.rs:8-108
-static Dict create_test_dict(int device) {
-    std::vector<std::string> keywords = {"テスト", "辞書", "形態素"};   // already in byte order
+struct Fixture {
+    std::vector<uint8_t> category;
+    int32_t* da = nullptr;
+    kp_dict_arrays arrays;
+    ~Fixture() { kp_da_free(da); }
+};
+
+static void fixture_arrays(Fixture* fx) {
+    static const std::vector<std::string> keywords = {"テスト", "辞書", "形態素"};   // already in byte order
     std::string blob;
     std::vector<uint64_t> off = {0};
     std::vector<int64_t> ids;
@@ -39,30 +46,29 @@ static Dict create_test_dict(int device) {
         off.push_back(blob.size());
         ids.push_back((int64_t)i + 1);
     }
-    int32_t* da = nullptr;
     uint64_t da_len = 0;
-    kanpyo::check(kp_da_build((const uint8_t*)blob.data(), off.data(), keywords.size(), ids.data(), &da, &da_len));
-    const int16_t morphs[] = {0, 0, 1000, 1, 1, 1200, 2, 2, 1100};
-    const int16_t conn[] = {0, 100, 200, 100, 0, 100, 200, 100, 0};
-    std::vector<uint8_t> category(1 << 16, 0);
-    for (uint32_t c = 0x3042; c <= 0x3093; c++) category[c] = 2;   // 'あ'..='ん' HIRAGANA
-    for (uint32_t c = 0x4E00; c <= 0x9FA5; c++) category[c] = 1;   // '一'..='龥' KANJI
-    const uint8_t invoke[] = {0, 1, 1}, group[] = {0, 1, 1};
-    const uint8_t unk_cat[] = {1, 2};
-    const int64_t unk_first[] = {1, 2};
-    const uint64_t unk_count[] = {1, 1};
-    const int16_t unk_morphs[] = {0, 0, 5000, 1, 1, 5000};
-    kp_dict_arrays a;
+    kanpyo::check(kp_da_build((const uint8_t*)blob.data(), off.data(), keywords.size(), ids.data(), &fx->da, &da_len));
+    static const int16_t morphs[] = {0, 0, 1000, 1, 1, 1200, 2, 2, 1100};
+    static const int16_t conn[] = {0, 100, 200, 100, 0, 100, 200, 100, 0};
+    fx->category.assign(1 << 16, 0);
+    for (uint32_t c = 0x3042; c <= 0x3093; c++) fx->category[c] = 2;   // 'あ'..='ん' HIRAGANA
+    for (uint32_t c = 0x4E00; c <= 0x9FA5; c++) fx->category[c] = 1;   // '一'..='龥' KANJI
+    static const uint8_t invoke[] = {0, 1, 1}, group[] = {0, 1, 1};
+    static const uint8_t unk_cat[] = {1, 2};
+    static const int64_t unk_first[] = {1, 2};
+    static const uint64_t unk_count[] = {1, 1};
+    static const int16_t unk_morphs[] = {0, 0, 5000, 1, 1, 5000};
+    kp_dict_arrays& a = fx->arrays;
     std::memset(&a, 0, sizeof(a));
-    a.da = da;
+    a.da = fx->da;
     a.da_len = da_len;
     a.morphs = morphs;
     a.n_morphs = 3;
     a.conn_row = 3;
     a.conn_col = 3;
     a.conn = conn;
-    a.char_category = category.data();
-    a.n_char_category = category.size();
+    a.char_category = fx->category.data();
+    a.n_char_category = fx->category.size();
     a.invoke_list = invoke;
     a.n_invoke = 3;
     a.group_list = group;
@@ -73,9 +79,6 @@ static Dict create_test_dict(int device) {
     a.n_unk_map = 2;
     a.unk_morphs = unk_morphs;
     a.n_unk_morphs = 2;
-    Dict d(a, device);
-    kp_da_free(da);
-    return d;
 }
 
 static void test_tokenizer_basic(Tokenizer& tokenizer) {           // src/tests.rs:111-129
@@ -137,6 +140,28 @@ static void test_batch_and_lattice(Tokenizer& tokenizer) {
     CHECK(la[6].dp == 5200 && la[6].pre == 1, "EOS dp / pre");
 }
 
+// ABI 2 from compiled host code: compact records + host expansion, both device paths, batches in flight, and the
+// single-process shard group (one device here) must all give the tokens of the plain call -- including the empty
+// paths of the fixture (no unknown entry for DEFAULT: 'x' has no node at all, EOS stays unreachable).
+static void test_abi2_paths(Tokenizer& tokenizer, const kp_dict_arrays& arrays, int device) {
+    const std::vector<std::string_view> inputs = {"テスト", "", "辞書テスト形態素", "あいうえお", "xテスト", "テストx", "x", "テxスト"};
+    const auto want = tokenizer.tokenize_batch(inputs);
+    CHECK(want[0].size() == 2 && want[2].size() == 4, "plain sentences");
+    CHECK(want[4].empty() && want[5].empty() && want[6].empty() && want[7].empty(), "a char without any node: dp[EOS] = INF, no token at all");
+    CHECK(tokenizer.tokenize_batch_compact(inputs) == want, "compact records == wide records");
+    for (int path : {KP_PATH_PIPELINE, KP_PATH_FUSED, KP_PATH_AUTO}) {
+        tokenizer.set_path(path);
+        CHECK(tokenizer.tokenize_batch(inputs) == want, "device paths agree");
+        CHECK(tokenizer.tokenize_batch_compact(inputs) == want, "device paths agree (compact)");
+    }
+    kanpyo::Queue queue(tokenizer.dict(), 2);
+    std::vector<uint64_t> tickets;
+    for (int k = 0; k < 2; k++) tickets.push_back(queue.submit(inputs));
+    for (uint64_t t : tickets) CHECK(queue.wait(t) == want, "queued batch == plain call");
+    kanpyo::Shards shards(arrays, {device});
+    CHECK(shards.tokenize_batch(inputs) == want, "shard group == plain call");
+}
+
 static void test_errors(Tokenizer& tokenizer) {
     bool threw = false;
     try {
@@ -150,13 +175,16 @@ static void test_errors(Tokenizer& tokenizer) {
 int main(int argc, char** argv) {
     const int device = argc > 1 ? std::atoi(argv[1]) : 0;
     try {
-        Tokenizer tokenizer(create_test_dict(device));
+        Fixture fx;
+        fixture_arrays(&fx);
+        Tokenizer tokenizer(Dict(fx.arrays, device));
         test_tokenizer_basic(tokenizer);
         test_tokenizer_empty_input(tokenizer);
         test_tokenizer_unknown_word(tokenizer);
         test_token_positions(tokenizer);
         test_tokenizer_dict_roundtrip(tokenizer, device);
         test_batch_and_lattice(tokenizer);
+        test_abi2_paths(tokenizer, fx.arrays, device);
         test_errors(tokenizer);
     } catch (const kanpyo::Error& e) {
         std::fprintf(stderr, "kanpyo::Error %d: %s\n", e.status(), e.what());

@@ -241,7 +241,8 @@ int run_pipeline(kp_tokenizer* t, kp_chunk& c, StageTimes* times) {
     if (t->count_work) KP_LAUNCH(kp_launch_pair_count(c, st));
     KP_CUDA(cudaEventRecord(t->ev[EV_VITERBI], st));
     KP_LAUNCH(kp_launch_backtrace_count(c, d, st));
-    KP_LAUNCH(kp_launch_backtrace_stage(c, st));
+    c.direct_emit = c.sel == nullptr;               // the whole chunk is here: no staging needed
+    if (!c.direct_emit) KP_LAUNCH(kp_launch_backtrace_stage(c, st));
     KP_CUDA(cudaEventRecord(t->ev[EV_BACKTRACE], st));
     t->counters.chars += c.C;
     t->counters.nodes += (uint64_t)c.N + S;   // + one BOS per sentence (not materialised on the device)
@@ -379,7 +380,8 @@ int chunk_compute(kp_tokenizer* t, kp_chunk& c, uint64_t* n_tokens, StageTimes* 
 
 int chunk_pack(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, bool compact) {
     cudaStream_t st = t->stream;
-    KP_LAUNCH(kp_launch_tokens_pack(c, tok_base, compact, st));
+    if (c.direct_emit) KP_LAUNCH(kp_launch_tokens_emit(c, tok_base, compact, st));
+    else KP_LAUNCH(kp_launch_tokens_pack(c, tok_base, compact, st));
     KP_CUDA(cudaEventRecord(t->ev[EV_PACK], st));
     return KP_OK;
 }

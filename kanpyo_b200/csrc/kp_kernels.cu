@@ -1309,6 +1309,53 @@ __global__ void __launch_bounds__(BT_THREADS) kp_tokens_pack(uint32_t S, const u
     }
 }
 
+// Pipeline-only chunks (no sentence went through the fused kernel) skip the staging area: the packed result is
+// written straight from the parked paths, a warp per sentence, each lane one token.
+template <bool COMPACT>
+__global__ void __launch_bounds__(BT_THREADS) kp_tokens_emit(uint32_t S, const uint32_t* __restrict__ coff,
+                                                             const uint4* __restrict__ rec, const uint4* __restrict__ binfo,
+                                                             const uint32_t* __restrict__ path,
+                                                             const uint32_t* __restrict__ toff, uint64_t tok_base,
+                                                             void* __restrict__ tok_off_out, void* __restrict__ tokens_out) {
+    const uint32_t s = (blockIdx.x * BT_THREADS + threadIdx.x) >> 5;
+    const uint32_t l = lane_id();
+    if (s > S) return;
+    if (l == 0) {
+        if (COMPACT) ((uint32_t*)tok_off_out)[s] = (uint32_t)(tok_base + toff[s]);
+        else ((uint64_t*)tok_off_out)[s] = tok_base + toff[s];
+    }
+    if (s == S) return;
+    const uint32_t bb = coff[s] + s;
+    const uint32_t sent_byte0 = binfo[bb].x;     // for n == 0 this is the EOS boundary: also the sentence start
+    const uint32_t w0 = toff[s], cnt = toff[s + 1] - w0;
+    for (uint32_t k = l; k < cnt; k += 32) {
+        const uint4 r = rec[path[bb + cnt - 1 - k]];
+        const uint32_t kind = r.x >> KP_KIND_SHIFT;
+        const uint32_t position = binfo[r.y].x - sent_byte0, start = r.y - bb;
+        if (!COMPACT) {
+            // {id, position, start, char_len | cls << 16}; EOS: char_len = "EOS".chars().count()
+            ((uint4*)tokens_out)[w0 + k] = make_uint4(r.x & KP_ID_MASK, position, start,
+                                                      (kind == KP_CLASS_DUMMY ? 3u : r.w >> 16) | (kind << 16));
+        } else {
+            uint32_t lens = start;                                               // EOS: n_chars
+            if (kind != KP_CLASS_DUMMY) {
+                const uint32_t len = r.w >> 16;                                  // chars; the next token starts len chars on
+                lens = ((binfo[r.y + len].x - binfo[r.y].x) & 0xFFFFu) | (len << 16);
+            }
+            ((uint2*)tokens_out)[w0 + k] = make_uint2((r.x & KP_ID_MASK) | (kind << KP_KIND_SHIFT), lens);
+        }
+    }
+}
+
+int kp_launch_tokens_emit(const kp_chunk& c, uint64_t tok_base, bool compact, cudaStream_t st) {
+    const uint32_t blocks = (uint32_t)(((uint64_t)(c.S_all + 1) * 32 + BT_THREADS - 1) / BT_THREADS);
+    if (compact)
+        kp_tokens_emit<true><<<blocks, BT_THREADS, 0, st>>>(c.S_all, c.coff, c.rec, c.binfo, c.path, c.toff32, tok_base, c.tok_off, c.tokens);
+    else
+        kp_tokens_emit<false><<<blocks, BT_THREADS, 0, st>>>(c.S_all, c.coff, c.rec, c.binfo, c.path, c.toff32, tok_base, c.tok_off, c.tokens);
+    return kp_launch_check("kp_tokens_emit");
+}
+
 int kp_launch_backtrace_count(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
     if (c.S == 0) return 0;
     kp_backtrace_find<<<(uint32_t)(((uint64_t)c.S * BT_GROUP + BT_THREADS - 1) / BT_THREADS), BT_THREADS, 0, st>>>(c.S, c.order, c.sel, c.coff, c.noff, c.boff, c.rec, c.ndp, c.bnode,

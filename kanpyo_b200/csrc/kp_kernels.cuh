@@ -41,6 +41,7 @@ struct kp_chunk {
     uint64_t base;           // off[0]
     uint32_t S, B;           // S = sentences of THIS pass (all of the chunk, or the `sel` subset)
     uint32_t S_all;          // sentences of the chunk
+    bool direct_emit;        // pipeline-only chunk: tokens go from the parked paths to the packed result, no staging
     const uint32_t* sel;     // [S] chunk sentence behind each slot of this pass (nullptr = identity); outputs
                              // (eos_cost, tcount, staged tokens) are indexed by chunk sentence
     uint32_t* sel_out;       // [S_all] list the fused path appends the sentences it leaves to the pipeline to
@@ -88,6 +89,8 @@ int kp_launch_backtrace_count(const kp_chunk& c, const kp_ddict& d, cudaStream_t
 int kp_launch_fill_pre(const kp_chunk& c, const kp_ddict& d, cudaStream_t st);
 int kp_launch_backtrace_stage(const kp_chunk& c, cudaStream_t st);
 int kp_launch_tokens_pack(const kp_chunk& c, uint64_t tok_base, bool compact, cudaStream_t st);
+// pipeline-only chunk: packed result straight from the parked paths (no staging)
+int kp_launch_tokens_emit(const kp_chunk& c, uint64_t tok_base, bool compact, cudaStream_t st);
 // exclusive scans, n inputs -> n+1 outputs; total (u64) written to *total
 int kp_launch_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint64_t* tmp, uint64_t* total, cudaStream_t st);
 int kp_launch_scan2(const uint32_t* in_a, const uint32_t* in_b, uint32_t* out_a, uint32_t* out_b, uint32_t n,

@@ -213,6 +213,10 @@ int kp_tokenizer_sync(kp_tokenizer* t);
  * KP_PATH_FUSED force one path for every batch size (measurements, parity tests). */
 enum { KP_PATH_AUTO = 0, KP_PATH_PIPELINE = 1, KP_PATH_FUSED = 2 };
 int kp_tokenizer_set_path(kp_tokenizer* t, int path);
+/* How the calling thread waits for the device.  0 (default): the driver spins (lowest latency).  1: the thread
+ * sleeps on a blocking-sync event -- for hosts where many contexts wait at once (a queue of three contexts per GPU
+ * on eight GPUs is 24 waiting threads) and spinning threads would starve each other. */
+int kp_tokenizer_set_blocking_sync(kp_tokenizer* t, int on);
 
 /* ---- asynchronous batches: H2D(n+1) || kernels(n) || D2H(n-1) across calls ------------------------
  * A queue owns `depth` independent tokenizer contexts (stream + scratch + pinned result buffers),
@@ -225,6 +229,7 @@ int kp_tokenizer_set_path(kp_tokenizer* t, int path);
 typedef struct kp_queue kp_queue;
 int kp_queue_create(const kp_dict* d, uint32_t depth, kp_queue** out);
 int kp_queue_set_path(kp_queue* q, int path);    /* kp_tokenizer_set_path on every context */
+int kp_queue_set_blocking_sync(kp_queue* q, int on);   /* kp_tokenizer_set_blocking_sync on every context */
 int kp_queue_submit(kp_queue* q, const uint8_t* utf8, const uint64_t* offsets, uint64_t n_sent, uint64_t* ticket);
 int kp_queue_wait(kp_queue* q, uint64_t ticket, kp_result8* out);
 void kp_queue_destroy(kp_queue* q);

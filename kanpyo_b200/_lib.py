@@ -86,6 +86,8 @@ SYMBOLS = {
     "kp_tokenizer_set_path": (C.c_int, [_P, C.c_int]),
     "kp_queue_create": (C.c_int, [_P, C.c_uint32, C.POINTER(_P)]),
     "kp_queue_set_path": (C.c_int, [_P, C.c_int]),
+    "kp_queue_set_blocking_sync": (C.c_int, [_P, C.c_int]),
+    "kp_tokenizer_set_blocking_sync": (C.c_int, [_P, C.c_int]),
     "kp_queue_submit": (C.c_int, [_P, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "kp_queue_wait": (C.c_int, [_P, C.c_uint64, C.POINTER(Result8)]),
     "kp_queue_destroy": (None, [_P]),

@@ -100,6 +100,8 @@ struct kp_tokenizer {
     DevBuf small_in, small_out;        // small-batch path: one staging block in, one block out
     PinBuf h_small_in, h_small_out;
     uint64_t small_calls = 0;
+    bool blocking_sync = false;        // wait on a blocking-sync event instead of spinning (many contexts per core)
+    cudaEvent_t ev_block = nullptr;
     uint32_t fused_max_batch = KP_FUSED_AUTO_SENTENCES;
     kp_perm perm = {};
     uint32_t perm_age = 0;     // passes since the column order was last ranked
@@ -136,6 +138,20 @@ namespace {
         t->profile.kernel_launches += rc__;  \
     } while (0)
 
+// Wait for everything queued on the tokenizer's stream.  Default: cudaStreamSynchronize (the driver spins: lowest
+// latency).  With blocking_sync the thread sleeps on a cudaEventBlockingSync event instead: a queue of three contexts
+// per GPU on eight GPUs is 24 waiting threads, and spinning ones starve each other on a 32-core host.
+static int kp_wait_stream(kp_tokenizer* t) {
+    if (!t->blocking_sync) {
+        KP_CUDA(cudaStreamSynchronize(t->stream));
+        return KP_OK;
+    }
+    if (!t->ev_block) KP_CUDA(cudaEventCreateWithFlags(&t->ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
+    KP_CUDA(cudaEventRecord(t->ev_block, t->stream));
+    KP_CUDA(cudaEventSynchronize(t->ev_block));
+    return KP_OK;
+}
+
 struct StageTimes {
     float prep = 0, lattice = 0, bucket = 0, viterbi = 0, backtrace = 0;
 };
@@ -167,7 +183,7 @@ int run_pipeline(kp_tokenizer* t, kp_chunk& c, StageTimes* times) {
     KP_LAUNCH(kp_launch_length_order(c, st));       // scan of the length histogram prep_count filled
     KP_CUDA(cudaMemcpyAsync(h_tot, c.totals, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaMemcpyAsync(h_err, c.err, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, st));
-    KP_CUDA(cudaStreamSynchronize(st));
+    KP_TRY(kp_wait_stream(t));
     if (h_err[1]) {
         kp_set_error("sentence offsets are not ascending or exceed the text length");
         return KP_ERR_ARG;
@@ -208,7 +224,7 @@ int run_pipeline(kp_tokenizer* t, kp_chunk& c, StageTimes* times) {
     KP_LAUNCH(kp_launch_lattice_count(c, d, t->count_work, st));
     KP_LAUNCH(kp_launch_scan2(c.ncount, c.bcount, c.noff, c.boff, c.NB, c.scan_tmp, &c.totals[1], &c.totals[2], st));
     KP_CUDA(cudaMemcpyAsync(h_tot, c.totals, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, st));
-    KP_CUDA(cudaStreamSynchronize(st));
+    KP_TRY(kp_wait_stream(t));
     if (h_tot[1] >= (1ull << 31) - 1) return KP_ERR_TOO_LARGE;   // node indices carry a flag in bit 31 (KP_SLOT_SHARED)
     c.N = (uint32_t)h_tot[1];
     if (h_tot[2] != h_tot[1]) {
@@ -289,7 +305,7 @@ int run_fused(kp_tokenizer* t, kp_chunk& c, uint32_t* left) {
     KP_CUDA(cudaMemcpyAsync(h_err, c.err, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaMemcpyAsync(h_ctl, fctl, sizeof(uint32_t) * 32, cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaMemcpyAsync(h_tot + 8, c.totals + 8, sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost, st));
-    KP_CUDA(cudaStreamSynchronize(st));
+    KP_TRY(kp_wait_stream(t));
     if (h_err[1]) {
         kp_set_error("sentence offsets are not ascending or exceed the text length");
         return KP_ERR_ARG;
@@ -358,7 +374,7 @@ int chunk_compute(kp_tokenizer* t, kp_chunk& c, uint64_t* n_tokens, StageTimes* 
     c.scan_tmp = t->scan_tmp.as<uint64_t>();
     KP_LAUNCH(kp_launch_scan(c.tcount, c.toff32, c.S_all, c.scan_tmp, &c.totals[3], st));
     KP_CUDA(cudaMemcpyAsync(h_tot, c.totals, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, st));
-    KP_CUDA(cudaStreamSynchronize(st));
+    KP_TRY(kp_wait_stream(t));
     *n_tokens = h_tot[3];
     t->counters.bytes += c.B;
     t->counters.tokens += h_tot[3];
@@ -482,6 +498,7 @@ extern "C" void kp_tokenizer_destroy(kp_tokenizer* t) {
     for (PinBuf* b : pins) b->release();
     for (int i = 0; i < EV_COUNT; i++)
         if (t->ev[i]) cudaEventDestroy(t->ev[i]);
+    if (t->ev_block) cudaEventDestroy(t->ev_block);
     if (t->fev_fork) cudaEventDestroy(t->fev_fork);
     for (uint32_t k = 0; k < KP_FUSED_MAX_CLASSES; k++) {
         if (t->fev_join[k]) cudaEventDestroy(t->fev_join[k]);
@@ -494,6 +511,12 @@ extern "C" void kp_tokenizer_destroy(kp_tokenizer* t) {
 extern "C" int kp_tokenizer_set_chunk_bytes(kp_tokenizer* t, uint64_t bytes) {
     if (!t || bytes == 0) return KP_ERR_ARG;
     t->chunk_bytes = std::min<uint64_t>(bytes, (1ull << 31) - 1);
+    return KP_OK;
+}
+
+extern "C" int kp_tokenizer_set_blocking_sync(kp_tokenizer* t, int on) {
+    if (!t) return KP_ERR_ARG;
+    t->blocking_sync = on != 0;
     return KP_OK;
 }
 
@@ -563,7 +586,7 @@ static int kp_tokenize_device(kp_tokenizer* t, const uint8_t* d_utf8, const uint
     StageTimes times;
     KP_TRY(run_chunk(t, c, 0, compact, n_tokens, &times));
     KP_CUDA(cudaEventRecord(t->ev[EV_END], st));
-    KP_CUDA(cudaEventSynchronize(t->ev[EV_END]));
+    KP_TRY(kp_wait_stream(t));
     store_times(t, times);
     cudaEventElapsedTime(&t->profile.total_ms, t->ev[EV_START], t->ev[EV_END]);
     *used = c;
@@ -686,7 +709,7 @@ int tokenize_small(kp_tokenizer* t, const uint8_t* utf8, const uint64_t* offsets
     KP_CUDA(cudaMemcpyAsync(dout, din, 272, cudaMemcpyDeviceToDevice, st));          // counters + flags ride out with the result
     KP_CUDA(cudaMemcpyAsync(t->h_small_out.p, dout, out_bytes, cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaEventRecord(t->ev[EV_END], st));
-    KP_CUDA(cudaEventSynchronize(t->ev[EV_END]));
+    KP_TRY(kp_wait_stream(t));
     const char* hout = (const char*)t->h_small_out.p;
     const uint64_t* r_tot = (const uint64_t*)hout;
     const uint32_t* r_err = (const uint32_t*)(hout + in_err);
@@ -790,7 +813,7 @@ static int kp_tokenize_host(kp_tokenizer* t, const uint8_t* utf8, const uint64_t
         KP_CUDA(cudaMemcpyAsync((char*)t->h_tok_off.p + off_sz * s0, c.tok_off, off_sz * (S + 1), cudaMemcpyDeviceToHost, st));
         KP_CUDA(cudaMemcpyAsync(t->h_eos.as<int32_t>() + s0, c.eos_cost, sizeof(int32_t) * S, cudaMemcpyDeviceToHost, st));
         KP_CUDA(cudaEventRecord(t->ev[EV_END], st));
-        KP_CUDA(cudaEventSynchronize(t->ev[EV_END]));
+        KP_TRY(kp_wait_stream(t));
         float ms = 0;
         cudaEventElapsedTime(&ms, t->ev[EV_START], t->ev[EV_H2D]);    h2d_ms += ms;
         cudaEventElapsedTime(&ms, t->ev[EV_PACK], t->ev[EV_END]);     d2h_ms += ms;

@@ -244,6 +244,16 @@ extern "C" int kp_queue_set_path(kp_queue* q, int path) {
     return KP_OK;
 }
 
+extern "C" int kp_queue_set_blocking_sync(kp_queue* q, int on) {
+    if (!q) return KP_ERR_ARG;
+    for (kp_queue_slot* s : q->slots) {
+        s->worker.wait();
+        int rc = kp_tokenizer_set_blocking_sync(s->tok, on);
+        if (rc) return rc;
+    }
+    return KP_OK;
+}
+
 extern "C" int kp_queue_submit(kp_queue* q, const uint8_t* utf8, const uint64_t* offsets, uint64_t n_sent,
                                uint64_t* ticket) {
     if (!q || !offsets || !ticket) return KP_ERR_ARG;

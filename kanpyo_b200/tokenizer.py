@@ -308,6 +308,10 @@ class Queue:
     def set_path(self, path: str):
         _lib.check(self._L.kp_queue_set_path(self._h, {"auto": 0, "pipeline": 1, "fused": 2}[path]))
 
+    def set_blocking_sync(self, on: bool):
+        """Worker threads sleep while the device works instead of spinning (many contexts per host core)."""
+        _lib.check(self._L.kp_queue_set_blocking_sync(self._h, 1 if on else 0))
+
     def submit_ptr(self, text_ptr: int, offsets_ptr: int, n_sent: int) -> int:
         tk = C.c_uint64()
         _lib.check(self._L.kp_queue_submit(self._h, text_ptr, offsets_ptr, n_sent, C.byref(tk)))

@@ -576,3 +576,42 @@ def test_fused_path_takes_the_short_sentences(gpu_tok, oracle_tok, vocab):
         c = gpu_tok.counters()
         assert (c["bytes"], c["chars"], c["nodes"], c["tokens"]) == (ctr["B"], ctr["C"], ctr["N"], ctr["T"])
         assert p["fused_sentences"] > 0.95 * n, p
+
+
+def test_fuzz_both_paths(gpu_ipadic, oracle_tok, vocab):
+    """Seeded random sentences glued from dictionary words and awkward pieces (long same-class runs, digits, ASCII,
+    4-byte characters, NUL, half-width kana, symbols), with byte lengths spread around the fused kernel's class limits
+    (192 ... 1536) so that size classes, overflow into the largest class and the hand-over to the pipeline all occur;
+    both device paths must give the oracle's tokens and costs, as one batch and in slices of 1, 7 and 64 sentences
+    (the one-round-trip path)."""
+    import kanpyo_b200
+    rng = np.random.default_rng(20261017)
+    words = [w.decode("utf-8") for w in vocab.words[:4000]]
+    pieces = ["ー" * 40, "ア" * 25, "123456789" * 3, "abc def ", "𠮷", "😀", "\x00", "ｶﾀｶﾅ", "。", "、", "・・・", "一二三", "ＡＢＣ", "々",
+              "する" * 12, "こと" * 10, "の" * 30, "東京都" * 8, "http://a.b/c?d=1", "　", "\t", "ゟ", "Привет", "αβγ"]
+    sents = []
+    for k in range(1500):
+        target = int(rng.choice([0, 3, 30, 150, 190, 200, 250, 262, 315, 330, 440, 460, 760, 780, 1500, 1560, 2500]))
+        s = ""
+        while len(s.encode("utf-8")) < target:
+            s += pieces[int(rng.integers(len(pieces)))] if rng.random() < 0.35 else words[int(rng.integers(len(words)))]
+        sents.append(s)
+    text, off = pack(sents)
+    o_off, o_tok, o_cost, _ = oracle_tok.tokenize_batch(text, off, threads=os.cpu_count() or 8)
+    t = kanpyo_b200.Tokenizer(gpu_ipadic, device=0)
+    try:
+        for path in ("fused", "pipeline", "auto"):
+            t.set_path(path)
+            assert_batch_equal(t.tokenize_batch_bytes(text, off), o_off, o_tok, o_cost)
+            if path == "fused":
+                p = t.profile()
+                assert 0.5 * len(sents) < p["fused_sentences"] < len(sents), p    # the > 1536-byte ones go to the pipeline
+        t.set_path("auto")
+        for width in (1, 7, 64):
+            for s0 in range(0, 448, width):
+                s1 = s0 + width
+                sub = t.tokenize_batch_bytes(text[int(off[s0]):int(off[s1])], off[s0:s1 + 1] - off[s0])
+                a, b = int(o_off[s0]), int(o_off[s1])
+                assert_batch_equal(sub, o_off[s0:s1 + 1] - o_off[s0], o_tok[a:b], o_cost[s0:s1])
+    finally:
+        t.close()

@@ -1197,35 +1197,43 @@ __global__ void __launch_bounds__(BT_THREADS) kp_backtrace_find(uint32_t S, cons
     uint32_t cnt = 0;
     int dp = ndp[cur];
     uint4 r = rec[cur];                          // {id|class, start boundary, left|right<<16, cost|len<<16}
+    // bucket of the current node's start boundary.  For every candidate the lanes also fetch ITS start bucket's
+    // bounds, next to the matrix cell (both depend only on the candidate's record): the winner's bounds arrive by
+    // shuffle and the next token starts one dependent load earlier (four levels per token -> three).
+    uint32_t q0 = boff[r.y], q1 = boff[r.y + 1];
     while (true) {
         if (dp >= KP_INF) break;                 // pre_nodes[pos] is None: no total < INF was ever seen
-        const uint32_t q0 = boff[r.y], q1 = boff[r.y + 1];
         const char* crow = (const char*)conn + (size_t)(r.z & 0xFFFFu) * conn_row * 2;   // connection.rs:12-14
         const int want = dp - (int)(int16_t)(r.w & 0xFFFFu);
         bool found = false;
-        uint32_t next = KP_NONE;
+        uint32_t next = KP_NONE, q0n = 0, q1n = 0;
         for (uint32_t j0 = q0; j0 < q1; j0 += BT_GROUP) {
             const uint32_t j = j0 + l;
             bool ok = false;
             uint32_t nd = KP_NONE;
             int dpj = 0;                         // BOS: dp None -> 0, morph (0,0,0)
             uint4 rn = make_uint4(0, 0, 0, 0);
+            uint32_t nq0 = 0, nq1 = 0;
             if (j < q1) {
                 nd = bnode[j];
                 if (nd != KP_NONE) {
                     dpj = ndp[nd];
                     rn = rec[nd];
+                    nq0 = boff[rn.y];
+                    nq1 = boff[rn.y + 1];
                 }
                 ok = dpj + ld_conn(crow + (rn.z >> 16) * 2u) == want;
             }
             const uint32_t m = (__ballot_sync(gmask, ok) >> gshift) & ((1u << BT_GROUP) - 1u);
             if (m) {                             // first match in list order; its lane already holds the
-                const uint32_t src = gshift + (uint32_t)__ffs(m) - 1;   // next node's record and dp
+                const uint32_t src = gshift + (uint32_t)__ffs(m) - 1;   // next node's record, dp and bucket bounds
                 next = __shfl_sync(gmask, nd, src);
                 dp = __shfl_sync(gmask, dpj, src);
                 r.y = __shfl_sync(gmask, rn.y, src);
                 r.z = __shfl_sync(gmask, rn.z, src);
                 r.w = __shfl_sync(gmask, rn.w, src);
+                q0n = __shfl_sync(gmask, nq0, src);
+                q1n = __shfl_sync(gmask, nq1, src);
                 found = true;
                 break;
             }
@@ -1235,6 +1243,8 @@ __global__ void __launch_bounds__(BT_THREADS) kp_backtrace_find(uint32_t S, cons
         cnt++;
         if (next == KP_NONE) break;              // reached BOS, which has no predecessor and is not emitted
         cur = next;
+        q0 = q0n;
+        q1 = q1n;
     }
     if (l == 0) tcount[sel ? sel[s] : s] = cnt;
 }

@@ -19,9 +19,10 @@ LIB = os.path.join(HERE, "libkanpyo_b200.so")
 # kanpyo_b200/_variants/libkanpyo_b200.<name>.so; KANPYO_B200_LIB=<path> makes _lib.load() use it.
 VARIANT_DIR = os.path.join(HERE, "_variants")
 SOURCES = ["kp_dict.cu", "kp_kernels.cu", "kp_fused.cu", "kp_api.cu", "kp_queue.cu", "kp_dictbuild.cpp"]
-HEADERS = ["kp_common.cuh", "kp_kernels.cuh", os.path.join("..", "..", "include", "kanpyo_b200.h")]
+HEADERS = ["kp_common.cuh", "kp_kernels.cuh", "kp_exports.map", os.path.join("..", "..", "include", "kanpyo_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-Xptxas", "-v", "-shared", "-cudart", "static", "-ldl", "-lpthread"]
+              "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-Xptxas", "-v", "-shared", "-cudart", "static", "-ldl", "-lpthread",
+              "-Xlinker", "--version-script=" + os.path.join(CSRC, "kp_exports.map")]
 
 
 def nvcc() -> str:

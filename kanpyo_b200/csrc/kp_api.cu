@@ -633,7 +633,7 @@ constexpr uint64_t KP_SMALL_SENT = 64, KP_SMALL_BYTES = 48 << 10;
 
 static inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
-int tokenize_small(kp_tokenizer* t, const uint8_t* utf8, const uint64_t* offsets, uint64_t n_sent, bool compact,
+static int tokenize_small(kp_tokenizer* t, const uint8_t* utf8, const uint64_t* offsets, uint64_t n_sent, bool compact,
                    uint64_t* n_tokens, const void** h_tok_off, const void** h_tokens, const int32_t** h_eos) {
     const uint32_t S = (uint32_t)n_sent, nc = t->fclasses.n;
     const uint64_t nbytes = offsets[n_sent] - offsets[0];

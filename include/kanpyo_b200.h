@@ -21,6 +21,13 @@
  *   kp_lattice_dump           <- Lattice::build + Lattice::viterbi (pub nodes/edges) src/lattice.rs:6-10,101,116
  *   kp_da_common_prefix       <- IndexTable::search_common_prefix_of                kanpyo-dict/src/index.rs:40-53
  *                                (DoubleArray::search_common_prefix_of              kanpyo-dict/src/trie/da.rs:155-182)
+ * New with ABI 2 (no counterpart in the reference, which is single-threaded and takes one line per call):
+ *   kp_tokenize_batch8 / kp_token8   the batch call with 8-byte transfer records (half the device-to-host bytes)
+ *   kp_queue_*                       successive batches in flight: copies hidden behind the neighbours' kernels
+ *   kp_shards_*                      every GPU of the box from one process (NCCL broadcast + sentence shards)
+ *   kp_gather_*                      the token gather for one-process-per-GPU launchers (NCCL send / recv)
+ * Threading: a kp_dict is immutable and shareable; a kp_tokenizer, kp_queue, kp_shards or kp_gather handle takes
+ * calls from one thread at a time (each owns its streams, scratch and result buffers).
  */
 #ifndef KANPYO_B200_H
 #define KANPYO_B200_H
@@ -208,14 +215,14 @@ int kp_tokenizer_sync(kp_tokenizer* t);
  *   the fused kernel  one warp owns one sentence from its bytes to its tokens in shared memory: one launch and,
  *                 for batches of at most 64 sentences / 48 KiB, ONE host round trip per call -- the path for
  *                 the reference's own call pattern (one line per call) and for small batches.
- * KP_PATH_AUTO (default) picks by batch size (fused up to 2048 sentences per chunk); sentences that do not fit
+ * KP_PATH_AUTO (default) picks by batch size (fused up to 4096 sentences per chunk, where the two paths cross); sentences that do not fit
  * the fused kernel's shared-memory budget go through the pipeline in the same call.  KP_PATH_PIPELINE and
  * KP_PATH_FUSED force one path for every batch size (measurements, parity tests). */
 enum { KP_PATH_AUTO = 0, KP_PATH_PIPELINE = 1, KP_PATH_FUSED = 2 };
 int kp_tokenizer_set_path(kp_tokenizer* t, int path);
 /* How the calling thread waits for the device.  0 (default): the driver spins (lowest latency).  1: the thread
- * sleeps on a blocking-sync event -- for hosts where many contexts wait at once (a queue of three contexts per GPU
- * on eight GPUs is 24 waiting threads) and spinning threads would starve each other. */
+ * sleeps on a blocking-sync event, leaving the core to others -- for hosts with fewer cores than waiting contexts.
+ * (Measured with 24 queue workers on a 32-core host: spinning 50.0 GB/s, sleeping 41.7 GB/s; hence the default.) */
 int kp_tokenizer_set_blocking_sync(kp_tokenizer* t, int on);
 
 /* ---- asynchronous batches: H2D(n+1) || kernels(n) || D2H(n-1) across calls ------------------------

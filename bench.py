@@ -139,12 +139,23 @@ def host_info():
 
 def bind_to_gpu_numa_node(gpu_index):
     """What `numactl --cpunodebind --membind` does for a one-process-per-GPU launch: run this rank (and first-touch its
-    pinned buffers) on the NUMA node its GPU hangs off, so the H2D / D2H of eight ranks do not all cross the socket
-    link.  Topology from NVML + sysfs; any failure leaves the affinity untouched.  Returns a description or None."""
+    pinned buffers) on the CPUs next to its GPU, so the H2D / D2H of eight ranks do not all cross the socket link.
+    Topology from NVML (the GPU's ideal CPU set), else sysfs (the PCI device's NUMA node); any failure leaves the
+    affinity untouched.  Returns a description or None."""
+    allowed = os.sched_getaffinity(0)
     try:
         import pynvml as nv
         nv.nvmlInit()
-        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(gpu_index)).busId
+        h = nv.nvmlDeviceGetHandleByIndex(gpu_index)
+        try:
+            words = nv.nvmlDeviceGetCpuAffinity(h, (max(allowed) // 64) + 1)
+            cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1} & allowed
+            if 2 <= len(cpus) < len(allowed):
+                os.sched_setaffinity(0, cpus)
+                return "NVML cpu affinity (%d of %d cpus)" % (len(cpus), len(allowed))
+        except Exception:   # noqa: BLE001
+            pass
+        bus = nv.nvmlDeviceGetPciInfo(h).busId
         bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
         if len(bus.split(":")[0]) == 8:            # NVML prints an 8-digit domain, sysfs a 4-digit one
             bus = bus[4:]
@@ -155,7 +166,7 @@ def bind_to_gpu_numa_node(gpu_index):
         for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
             a, _, b = part.partition("-")
             cpus.update(range(int(a), int(b or a) + 1))
-        cpus &= os.sched_getaffinity(0)
+        cpus &= allowed
         if len(cpus) < 2:
             return None
         os.sched_setaffinity(0, cpus)

@@ -460,6 +460,18 @@ def product_arm(args):
     e2e_total_s = time.perf_counter() - t0
     barrier()
     e2e_result = copy_result8(r_e2e)
+    # what a caller that wants the 16-byte kp_token records (absolute position / start) pays on top: kp_expand_tokens8
+    # over the step's pinned result, one host thread (the Rust shim does this while it builds its Vec<Token>)
+    import ctypes as C
+    from kanpyo_b200 import _lib as kp_lib
+    from kanpyo_b200.tokenizer import TOKEN_DTYPE
+    expanded = np.empty(int(r_e2e.n_tokens), TOKEN_DTYPE)
+    expand_ms = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        kp_lib.check(kp_lib.load().kp_expand_tokens8(C.byref(r_e2e), C.c_void_p(h_off.data_ptr()), C.c_void_p(expanded.ctypes.data)))
+        dt = (time.perf_counter() - t0) * 1e3
+        expand_ms = dt if expand_ms is None else min(expand_ms, dt)
     # the synchronous call (one batch at a time, nothing overlapped), for comparison
     for _ in range(args.warmup):
         tk.tokenize_batch8_ptr(h_text.data_ptr(), h_off.data_ptr(), S)
@@ -629,10 +641,11 @@ def product_arm(args):
                     "h2d_bytes_per_step": int(world_h2d), "d2h_bytes_per_step": int(world_d2h),
                     "ms_per_step": e2e_total_ms / K,
                     "queue_workers_wait": "blocking" if blocking else "spinning",
+                    "expand_tokens8_ms_per_step": expand_ms,
                     "api": "kp_queue_submit / kp_queue_wait (C ABI), depth %d: pinned host text + offsets in, pinned host "
                            "kp_token8 records + offsets + dp[EOS] out, every step's copies inside the wall clock and "
                            "overlapped with the neighbouring steps' kernels; the records are the packed form the Rust "
-                           "shim expands into Vec<Token> (that expansion is host work and not in this number)"
+                           "shim expands into Vec<Token> (that expansion is host work and not in this number: expand_tokens8_ms_per_step is kp_expand_tokens8 over one step's result on one host thread, rank 0)"
                            % args.queue_depth,
                     "sync_call": {"value": world_bytes * K / (sync_total_ms * 1e-3), "ms_per_step": sync_total_ms / K,
                                   "api": "kp_tokenize_batch8, one blocking call per step, nothing overlapped"}},

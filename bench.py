@@ -461,7 +461,7 @@ def product_arm(args):
     barrier()
     e2e_result = copy_result8(r_e2e)
     # what a caller that wants the 16-byte kp_token records (absolute position / start) pays on top: kp_expand_tokens8
-    # over the step's pinned result, one host thread (the Rust shim does this while it builds its Vec<Token>)
+    # over the step's pinned result, up to 8 host threads (the Rust shim does this while it builds its Vec<Token>)
     import ctypes as C
     from kanpyo_b200 import _lib as kp_lib
     from kanpyo_b200.tokenizer import TOKEN_DTYPE
@@ -645,7 +645,7 @@ def product_arm(args):
                     "api": "kp_queue_submit / kp_queue_wait (C ABI), depth %d: pinned host text + offsets in, pinned host "
                            "kp_token8 records + offsets + dp[EOS] out, every step's copies inside the wall clock and "
                            "overlapped with the neighbouring steps' kernels; the records are the packed form the Rust "
-                           "shim expands into Vec<Token> (that expansion is host work and not in this number: expand_tokens8_ms_per_step is kp_expand_tokens8 over one step's result on one host thread, rank 0)"
+                           "shim expands into Vec<Token> (that expansion is host work and not in this number: expand_tokens8_ms_per_step is kp_expand_tokens8 over one step's result on up to 8 host threads, best of 3)"
                            % args.queue_depth,
                     "sync_call": {"value": world_bytes * K / (sync_total_ms * 1e-3), "ms_per_step": sync_total_ms / K,
                                   "api": "kp_tokenize_batch8, one blocking call per step, nothing overlapped"}},

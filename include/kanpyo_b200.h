@@ -197,7 +197,8 @@ int kp_tokenize_batch8(kp_tokenizer* t, const uint8_t* utf8, const uint64_t* off
 int kp_tokenize_batch_device8(kp_tokenizer* t, const uint8_t* d_utf8, const uint64_t* d_offsets, uint64_t n_sent,
                               uint64_t first_offset, uint64_t n_bytes, kp_result8* out);
 /* Host-side expansion kp_token8 -> kp_token (fills position / start / char_len; EOS char_len = 3).
- * offsets = the caller's sentence offsets [n_sent+1]; out has r->n_tokens entries.  Pure host code. */
+ * offsets = the caller's sentence offsets [n_sent+1]; out has r->n_tokens entries.  Pure host code; results of
+ * more than 2^18 tokens are split over up to 8 host threads (contiguous sentence ranges). */
 int kp_expand_tokens8(const kp_result8* r, const uint64_t* offsets, kp_token* out);
 int kp_last_counters(const kp_tokenizer* t, kp_counters* out);
 /* on != 0: also count P, P_ok, E (slower; never enabled inside a timed region). */

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "kp_kernels.cuh"
@@ -906,9 +907,9 @@ extern "C" int kp_tokenize_batch8(kp_tokenizer* t, const uint8_t* utf8, const ui
 
 // kp_token8 -> kp_token on the host: walk every sentence's tokens backwards from its EOS token
 // (position = sentence bytes, start = n_chars carried by the EOS record); see the header.
-extern "C" int kp_expand_tokens8(const kp_result8* r, const uint64_t* offsets, kp_token* out) {
-    if (!r || !offsets || (r->n_tokens && (!out || !r->tokens)) || (r->n_sent && !r->tok_off)) return KP_ERR_ARG;
-    for (uint64_t s = 0; s < r->n_sent; s++) {
+// Sentences [s0, s1); returns the first sentence whose last record is not EOS, or UINT64_MAX.
+static uint64_t kp_expand_range(const kp_result8* r, const uint64_t* offsets, kp_token* out, uint64_t s0, uint64_t s1) {
+    for (uint64_t s = s0; s < s1; s++) {
         const uint32_t a = r->tok_off[s], b = r->tok_off[s + 1];
         if (a == b) continue;                     // empty path (dp[EOS] = INF): no tokens, no EOS
         uint32_t pos = (uint32_t)(offsets[s + 1] - offsets[s]), start = 0;
@@ -920,10 +921,7 @@ extern "C" int kp_expand_tokens8(const kp_result8* r, const uint64_t* offsets, k
             o.cls = (uint8_t)cls;
             o.reserved = 0;
             if (k == b - 1) {
-                if (cls != KP_CLASS_DUMMY) {
-                    kp_set_error("sentence %llu: last token is not EOS", (unsigned long long)s);
-                    return KP_ERR_ARG;
-                }
+                if (cls != KP_CLASS_DUMMY) return s;
                 start = (uint32_t)x.byte_len | ((uint32_t)x.char_len << 16);
                 o.char_len = 3;
             } else {
@@ -935,6 +933,34 @@ extern "C" int kp_expand_tokens8(const kp_result8* r, const uint64_t* offsets, k
             o.start = start;
             out[k] = o;
         }
+    }
+    return UINT64_MAX;
+}
+
+// Large results are split over a few host threads (contiguous sentence ranges of about equal token
+// counts): one thread streams ~12 GB/s of records, a batch of 2M tokens would take it 4 ms.
+extern "C" int kp_expand_tokens8(const kp_result8* r, const uint64_t* offsets, kp_token* out) {
+    if (!r || !offsets || (r->n_tokens && (!out || !r->tokens)) || (r->n_sent && !r->tok_off)) return KP_ERR_ARG;
+    const uint64_t per_thread = 1u << 17;
+    uint64_t nthr = std::min<uint64_t>({r->n_tokens / per_thread, (uint64_t)std::thread::hardware_concurrency(), 8});
+    uint64_t bad = UINT64_MAX;
+    if (nthr <= 1) {
+        bad = kp_expand_range(r, offsets, out, 0, r->n_sent);
+    } else {
+        std::vector<uint64_t> cut(nthr + 1, r->n_sent), first(nthr, UINT64_MAX);
+        cut[0] = 0;
+        for (uint64_t i = 1; i < nthr; i++)       // first sentence starting at or after the i-th share of the tokens
+            cut[i] = (uint64_t)(std::lower_bound(r->tok_off, r->tok_off + r->n_sent, (uint32_t)(r->n_tokens * i / nthr)) - r->tok_off);
+        std::vector<std::thread> th;
+        for (uint64_t i = 1; i < nthr; i++)
+            th.emplace_back([&, i] { first[i] = kp_expand_range(r, offsets, out, cut[i], cut[i + 1]); });
+        first[0] = kp_expand_range(r, offsets, out, cut[0], cut[1]);
+        for (auto& x : th) x.join();
+        for (uint64_t i = 0; i < nthr; i++) bad = std::min(bad, first[i]);
+    }
+    if (bad != UINT64_MAX) {
+        kp_set_error("sentence %llu: last token is not EOS", (unsigned long long)bad);
+        return KP_ERR_ARG;
     }
     return KP_OK;
 }

@@ -452,6 +452,47 @@ def test_expand_tokens8_rebuilds_positions(oracle_mod, oracle_tok, vocab):
     assert any((np.diff(o_off) == 0).any() for _ in [0])      # the fixture batch holds empty paths
 
 
+def test_expand_tokens8_large_result_uses_threads_and_agrees():
+    """Above 2^18 tokens kp_expand_tokens8 splits the sentences over host threads: same records as the numpy
+    mirror on a synthetic result (ragged sentences, empty paths in between), and a sentence whose last record
+    is not EOS is still reported by number."""
+    from kanpyo_b200 import _lib
+    from kanpyo_b200.tokenizer import TOKEN8_DTYPE, TOKEN_DTYPE, expand_tokens8
+    rng = np.random.default_rng(7)
+    n_sent = 40_000
+    counts = rng.integers(0, 40, n_sent)                       # tokens before EOS; 0 with no EOS = empty path
+    empty = rng.random(n_sent) < 0.02
+    per = np.where(empty, 0, counts + 1)
+    tok_off = np.zeros(n_sent + 1, np.uint32)
+    tok_off[1:] = np.cumsum(per)
+    nt = int(tok_off[-1])
+    assert nt > (1 << 19)
+    t8 = np.zeros(nt, TOKEN8_DTYPE)
+    t8["id_cls"] = rng.integers(1, 1 << 20, nt).astype(np.uint32) | (np.uint32(1) << 30)
+    t8["byte_len"] = rng.integers(1, 13, nt)
+    t8["char_len"] = rng.integers(1, 5, nt)
+    last = tok_off[1:][per > 0] - 1
+    sent_of = np.repeat(np.arange(n_sent), per)
+    body = np.ones(nt, bool); body[last] = False
+    nbytes = np.bincount(sent_of[body], t8["byte_len"][body], n_sent).astype(np.uint64)
+    nchars = np.bincount(sent_of[body], t8["char_len"][body], n_sent).astype(np.uint32)
+    t8["id_cls"][last] = 0                                     # EOS: class Dummy, n_chars in the two length fields
+    t8["byte_len"][last] = nchars[per > 0] & 0xFFFF
+    t8["char_len"][last] = nchars[per > 0] >> 16
+    off = np.zeros(n_sent + 1, np.uint64)
+    off[1:] = np.cumsum(nbytes + rng.integers(0, 3, n_sent).astype(np.uint64))   # some paths start after byte 0
+    full = expand_tokens8(tok_off, t8, off)
+    L = _lib.load()
+    r = _lib.Result8(n_sent=n_sent, n_tokens=nt, tok_off=tok_off.ctypes.data, tokens=t8.ctypes.data, eos_cost=None)
+    out = np.zeros(nt, TOKEN_DTYPE)
+    _lib.check(L.kp_expand_tokens8(C.byref(r), off.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+    assert np.array_equal(out, full)
+    victim = int(np.flatnonzero(per > 0)[-3])
+    t8["id_cls"][tok_off[victim + 1] - 1] = np.uint32(1) << 30
+    assert L.kp_expand_tokens8(C.byref(r), off.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)) == -1
+    assert ("sentence %d" % victim) in L.kp_last_error().decode()
+
+
 def test_blob_is_refused_unless_it_is_what_pack_wrote(oracle_mod):
     """kp_dict_create_from_blob validates before it touches a device: a flipped payload byte,
     a truncated blob, a section pointing outside the blob or a stale layout version all give KP_ERR_BLOB."""

@@ -1156,8 +1156,8 @@ int kp_launch_pair_count(const kp_chunk& c, cudaStream_t st) {
 }
 
 // =================================================================================================
-// Back-trace (lattice.rs:144-153) + Node -> Token (tokenizer.rs:22-43).  8 lanes per sentence.
-// Pass 1 walks from the EOS node; the lanes test 8 candidate predecessors at a time for
+// Back-trace (lattice.rs:144-153) + Node -> Token (tokenizer.rs:22-43).  8 / 16 / 32 lanes per sentence.
+// Pass 1 walks from the EOS node; the lanes test that many candidate predecessors at a time for
 // dp[j] + conn + cost == dp[i] and a ballot picks the first (list order), which is the predecessor the
 // reference's strict '<' update keeps.  The path (node indices, back to front) is parked in `path`;
 // pass 2 (after the scan of the path lengths) writes the tokens front to back.
@@ -1167,13 +1167,13 @@ int kp_launch_pair_count(const kp_chunk& c, cudaStream_t st) {
 #endif
 constexpr int BT_THREADS = KP_BT_THREADS;
 #ifndef KP_BT_GROUP
-#define KP_BT_GROUP 8
+#define KP_BT_GROUP 0          // lanes per sentence; 0 = chosen per batch (kp_launch_backtrace_count)
 #endif
-constexpr int BT_GROUP = KP_BT_GROUP;
 
 #ifndef KP_BT_ORDER
 #define KP_BT_ORDER 1
 #endif
+template <int BT_GROUP>
 __global__ void __launch_bounds__(BT_THREADS) kp_backtrace_find(uint32_t S, const uint32_t* __restrict__ order,
                                                                 const uint32_t* __restrict__ sel,
                                                                 const uint32_t* __restrict__ coff,
@@ -1191,7 +1191,8 @@ __global__ void __launch_bounds__(BT_THREADS) kp_backtrace_find(uint32_t S, cons
     // the same length, and the long paths start first
     const uint32_t s = KP_BT_ORDER ? order[slot] : slot;
     const uint32_t l = threadIdx.x & (BT_GROUP - 1), gshift = lane_id() & ~(uint32_t)(BT_GROUP - 1);
-    const uint32_t gmask = ((1u << BT_GROUP) - 1u) << gshift;
+    constexpr uint32_t GM = BT_GROUP == 32 ? KP_FULL : ((1u << (BT_GROUP & 31)) - 1u);
+    const uint32_t gmask = GM << gshift;
     const uint32_t bb = coff[s] + s, n = coff[s + 1] - coff[s];
     uint32_t cur = noff[bb + n];                 // `self.nodes.len() - 1`: the EOS node
     uint32_t cnt = 0;
@@ -1224,7 +1225,7 @@ __global__ void __launch_bounds__(BT_THREADS) kp_backtrace_find(uint32_t S, cons
                 }
                 ok = dpj + ld_conn(crow + (rn.z >> 16) * 2u) == want;
             }
-            const uint32_t m = (__ballot_sync(gmask, ok) >> gshift) & ((1u << BT_GROUP) - 1u);
+            const uint32_t m = (__ballot_sync(gmask, ok) >> gshift) & GM;
             if (m) {                             // first match in list order; its lane already holds the
                 const uint32_t src = gshift + (uint32_t)__ffs(m) - 1;   // next node's record, dp and bucket bounds
                 next = __shfl_sync(gmask, nd, src);
@@ -1366,10 +1367,23 @@ int kp_launch_tokens_emit(const kp_chunk& c, uint64_t tok_base, bool compact, cu
     return kp_launch_check("kp_tokens_emit");
 }
 
+// Lanes per sentence: the widest group that keeps the batch within ~2.6 waves of resident warps (148 SMs x 64 warps).
+// A walk is a chain of dependent loads per token, and a bucket larger than the group takes several rounds of that
+// chain: wide groups shorten every chain, narrow groups keep more chains resident.  Measured (cfg2, back-trace ms,
+// 8 / 16 / 32 lanes): 65 536 sentences 0.195 / 0.227 / 0.272; 32 768: 0.156 / 0.123 / 0.151; 16 384: 0.141 / 0.111 /
+// 0.086; cfg4 (4096 long lines): 3.08 / 2.13 / 1.51.  Results do not depend on the choice.
 int kp_launch_backtrace_count(const kp_chunk& c, const kp_ddict& d, cudaStream_t st) {
     if (c.S == 0) return 0;
-    kp_backtrace_find<<<(uint32_t)(((uint64_t)c.S * BT_GROUP + BT_THREADS - 1) / BT_THREADS), BT_THREADS, 0, st>>>(c.S, c.order, c.sel, c.coff, c.noff, c.boff, c.rec, c.ndp, c.bnode,
-                                                         d.conn, d.conn_row, c.path, c.tcount);
+    const int group = KP_BT_GROUP ? KP_BT_GROUP : (c.S <= 25000 ? 32 : c.S <= 50000 ? 16 : 8);
+    const uint32_t blocks = (uint32_t)(((uint64_t)c.S * group + BT_THREADS - 1) / BT_THREADS);
+#define KP_BT_LAUNCH(G)                                                                                                    \
+    kp_backtrace_find<G><<<blocks, BT_THREADS, 0, st>>>(c.S, c.order, c.sel, c.coff, c.noff, c.boff, c.rec, c.ndp, c.bnode, \
+                                                        d.conn, d.conn_row, c.path, c.tcount)
+    if (group == 8) KP_BT_LAUNCH(8);
+    else if (group == 16) KP_BT_LAUNCH(16);
+    else if (group == 4) KP_BT_LAUNCH(4);
+    else KP_BT_LAUNCH(32);
+#undef KP_BT_LAUNCH
     return kp_launch_check("kp_backtrace_find");
 }
 

@@ -934,7 +934,8 @@ __device__ __forceinline__ uint64_t elem_ptr_pinned(const int16_t* base, uint32_
     asm volatile("mad.wide.u32 %0, %1, 2, %2;" : "=l"(r) : "r"(i), "l"(base));
     return r;
 }
-// *(int16*)(p + 2 * off): address = one IMAD.WIDE with an immediate multiplier
+// *(int16*)(p + 2 * off).  ptxas emits LEA + LEA.HI.X for the address (it keeps the two halves of p in unpaired
+// registers, which rules out IMAD.WIDE; a multiplier it cannot fold makes it three instructions -- both measured)
 __device__ __forceinline__ int ld_conn_at(uint64_t p, uint32_t off) {
     uint64_t a;
     int v;
@@ -959,8 +960,8 @@ __device__ __forceinline__ int ld_conn(const char* p) {
 //   dp[i] = min(best + cost_i, INF), kept only if < INF                             lattice.rs:127-139
 // The loop bound is the warp's largest bucket; lanes without a target and groups whose own bucket is
 // exhausted have their loads predicated off, so the memory traffic is each group's own.  Per pair
-// the loop issues five instructions: predicate, 8-byte bucket entry at an immediate offset, row
-// address (one IMAD.WIDE), 2-byte matrix cell, VIADDMNMX.
+// the loop issues six instructions: predicate, 8-byte bucket entry at an immediate offset, row
+// address (LEA + LEA.HI.X), 2-byte matrix cell, VIADDMNMX.
 // The argmin (pre_nodes) is NOT tracked here: the back-trace recomputes it for the ~30 nodes per
 // sentence that lie on the best path.  dp goes to ndp[i] and into the node's reduced slot: a plain
 // store for a known node (the slot is its own), a min-merge for an unknown node (the slot is shared
@@ -1051,7 +1052,7 @@ __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
                     if (u < rem) e[u] = rp[u];
 #pragma unroll
                 for (int u = 0; u < VIT_UNROLL; u++)
-                    if (u < rem) cell[u] = ld_conn_at(crow, (uint32_t)e[u].y);   // one IMAD.WIDE: crow + 2 * offset
+                    if (u < rem) cell[u] = ld_conn_at(crow, (uint32_t)e[u].y);   // crow + 2 * offset
 #pragma unroll
                 for (int u = 0; u < VIT_UNROLL; u++)
                     if (u < rem) best = __viaddmin_s32(e[u].x, cell[u], best);

@@ -1081,10 +1081,12 @@ __global__ void __launch_bounds__(VIT_THREADS, KP_VIT_MINB) kp_viterbi(
 // Lanes per sentence: 8 when the batch alone fills the machine with warps (148 SMs x 40 resident
 // warps), more when it does not -- a batch of few, long sentences (BASELINE.json configs[3]) is a few
 // thousand sequential chains, and what matters then is the length of each chain, not lane use.
+// Measured (cfg2, sweep ms, 8 / 16 / 32 lanes): 65 536 sentences 0.508 / 0.602 / 0.992; 32 768: 0.317 / 0.316 /
+// 0.508; 24 576: 0.307 / 0.258 / 0.391; 16 384: 0.287 / 0.199 / 0.264; 8 192: 0.255 / 0.178 / 0.162.
 // Results do not depend on the choice.
 int kp_launch_viterbi(const kp_chunk& c, const kp_ddict& d, const kp_perm& pm, cudaStream_t st) {
     if (c.S == 0) return 0;
-    const int group = KP_VIT_GROUP ? KP_VIT_GROUP : (c.S >= 24000 ? 8 : c.S >= 12000 ? 16 : 32);
+    const int group = KP_VIT_GROUP ? KP_VIT_GROUP : (c.S >= 30000 ? 8 : c.S >= 12000 ? 16 : 32);
     const uint32_t blocks = (uint32_t)(((uint64_t)c.S * group + VIT_THREADS - 1) / VIT_THREADS);
 #define KP_VIT_LAUNCH(G)                                                                                          \
     kp_viterbi<G><<<blocks, VIT_THREADS, 0, st>>>(c.S, c.N, c.order, c.sel, c.coff, c.noff, c.rbk, c.tgt, c.red, c.ndp, c.eos_cost, \

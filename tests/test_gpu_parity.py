@@ -173,10 +173,12 @@ def test_corpus_parity(gpu_tok, oracle_tok, vocab, kind, n):
     assert (c["bytes"], c["chars"], c["nodes"], c["tokens"]) == (ctr["B"], ctr["C"], ctr["N"], ctr["T"])
 
 
-@pytest.mark.parametrize("n", [13000, 26000])
+@pytest.mark.parametrize("n", [13000, 26000, 34000])
 def test_batch_size_does_not_change_results(gpu_tok, oracle_tok, vocab, n):
-    """kp_launch_viterbi picks its lanes per sentence from the batch size (32 below 12 000 sentences, 16 below
-    24 000, 8 above): every choice must give the reference's tokens and costs."""
+    """kp_launch_viterbi and kp_launch_backtrace_count pick their lanes per sentence from the batch size (sweep: 32
+    below 12 000 sentences, 16 below 30 000, 8 above; back-trace: 32 up to 25 000, 16 up to 50 000, 8 above): every
+    combination must give the reference's tokens and costs (the small batches and the 65 536-sentence batch of the
+    other tests cover 32 / 32 and 8 / 8; these cover 16 / 32, 16 / 16 and 8 / 16)."""
     from kanpyo_b200 import corpus
     text, off = corpus.synth_corpus(vocab, n, "cfg2")
     res = gpu_tok.tokenize_batch_bytes(text, off)

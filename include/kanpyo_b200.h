@@ -216,7 +216,7 @@ int kp_tokenizer_sync(kp_tokenizer* t);
  *   the fused kernel  one warp owns one sentence from its bytes to its tokens in shared memory: one launch and,
  *                 for batches of at most 64 sentences / 48 KiB, ONE host round trip per call -- the path for
  *                 the reference's own call pattern (one line per call) and for small batches.
- * KP_PATH_AUTO (default) picks by batch size (fused up to 4096 sentences per chunk, where the two paths cross); sentences that do not fit
+ * KP_PATH_AUTO (default) picks by batch size (fused up to 3584 sentences per chunk, where the two paths cross); sentences that do not fit
  * the fused kernel's shared-memory budget go through the pipeline in the same call.  KP_PATH_PIPELINE and
  * KP_PATH_FUSED force one path for every batch size (measurements, parity tests). */
 enum { KP_PATH_AUTO = 0, KP_PATH_PIPELINE = 1, KP_PATH_FUSED = 2 };

@@ -76,7 +76,8 @@ struct PinBuf {   // pinned host memory, preserved on growth
 
 constexpr uint32_t KP_PERM_REFRESH = 16;
 #ifndef KP_FUSED_AUTO_SENTENCES
-#define KP_FUSED_AUTO_SENTENCES 4096   // KP_PATH_AUTO: batches up to this many sentences take the fused kernel
+#define KP_FUSED_AUTO_SENTENCES 3584   // KP_PATH_AUTO: batches up to this many sentences take the fused kernel (the paths cross
+                                       // between 3072 and 4096 sentences, profiles/r02_device_sweep.txt)
 #endif
 #ifndef KP_FUSED_BYTES
 #define KP_FUSED_BYTES 192, 256, 320, 448, 768, 1536     // byte limits of the fused kernel's size classes

@@ -563,7 +563,7 @@ def test_both_paths_on_edge_cases(gpu_ipadic, oracle_tok, oracle_mod, path):
 def test_fused_path_takes_the_short_sentences(gpu_tok, oracle_tok, vocab):
     """On the cfg2 / cfg3 corpora nearly every sentence fits a size class of the fused kernel; the rest goes
     through the pipeline in the same call, and the packed result is the oracle's either way.  `auto` takes
-    the fused kernel for batches of up to 4096 sentences (one round trip up to 64), the pipeline above."""
+    the fused kernel for batches of up to 3584 sentences (one round trip up to 64), the pipeline above."""
     from kanpyo_b200 import corpus
     for kind, n, path in (("cfg2", 8000, "fused"), ("cfg3", 8000, "fused"), ("cfg2", 3000, "auto"), ("cfg3", 40, "auto")):
         text, off = corpus.synth_corpus(vocab, n, kind, seed=21)

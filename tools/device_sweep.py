@@ -9,7 +9,7 @@ d = builder.ipadic()
 vocab = corpus.Vocabulary(d.keywords, d.morphs)
 text, off = corpus.synth_corpus(vocab, 65536, "cfg2")
 tk = kanpyo_b200.Tokenizer(d, device=0)
-for n in (1024, 2048, 4096, 6144, 8192, 12288, 16384, 32768):
+for n in (256, 512, 1024, 2048, 3072, 4096, 5120, 6144, 8192):
     t_ = torch.from_numpy(text[:int(off[n])].copy()).cuda()
     o_ = torch.from_numpy(off[:n + 1].astype(np.int64)).cuda()
     torch.cuda.synchronize()

@@ -329,8 +329,15 @@ int run_fused(kp_tokenizer* t, kp_chunk& c, uint32_t* left) {
 // One device pass over a chunk whose text / offsets are already in device memory, in two halves so
 // that a multi-GPU caller can learn every shard's token count before any shard packs its result:
 //   chunk_compute  lattice, Viterbi, back-trace; tokens staged; token counts scanned; *n_tokens read back
+//                  (single-GPU calls hand it the token base and it queues chunk_pack before waiting)
 //   chunk_pack     staged tokens -> c.tok_off / c.tokens (offsets rebased by tok_base); c.eos_cost is final
-int chunk_compute(kp_tokenizer* t, kp_chunk& c, uint64_t* n_tokens, StageTimes* times) {
+int chunk_pack(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, bool compact);
+
+// pack_base: the chunk's token base when the caller already knows it (single-GPU calls), nullptr otherwise.  With a
+// known base the pack kernel is queued BEHIND the scan before the host waits for the token count, so the round trip
+// hides behind it.
+int chunk_compute(kp_tokenizer* t, kp_chunk& c, uint64_t* n_tokens, StageTimes* times, const uint64_t* pack_base = nullptr,
+                  bool compact = false) {
     cudaStream_t st = t->stream;
     const uint32_t S = c.S;
     c.S_all = S;
@@ -376,6 +383,10 @@ int chunk_compute(kp_tokenizer* t, kp_chunk& c, uint64_t* n_tokens, StageTimes* 
     c.scan_tmp = t->scan_tmp.as<uint64_t>();
     KP_LAUNCH(kp_launch_scan(c.tcount, c.toff32, c.S_all, c.scan_tmp, &c.totals[3], st));
     KP_CUDA(cudaMemcpyAsync(h_tot, c.totals, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, st));
+    if (pack_base) {
+        KP_TRY(chunk_pack(t, c, *pack_base, compact));
+        KP_CUDA(cudaEventRecord(t->ev[EV_END], st));      // end of the device work (a host caller records it again after its D2H)
+    }
     KP_TRY(kp_wait_stream(t));
     *n_tokens = h_tot[3];
     t->counters.bytes += c.B;
@@ -405,8 +416,7 @@ int chunk_pack(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, bool compact) {
 }
 
 int run_chunk(kp_tokenizer* t, kp_chunk& c, uint64_t tok_base, bool compact, uint64_t* n_tokens, StageTimes* times) {
-    KP_TRY(chunk_compute(t, c, n_tokens, times));
-    return chunk_pack(t, c, tok_base, compact);
+    return chunk_compute(t, c, n_tokens, times, &tok_base, compact);
 }
 
 void begin_call(kp_tokenizer* t) {
@@ -586,9 +596,7 @@ static int kp_tokenize_device(kp_tokenizer* t, const uint8_t* d_utf8, const uint
     c.tokens = t->d_tokens.p;
     KP_CUDA(cudaEventRecord(t->ev[EV_START], st));
     StageTimes times;
-    KP_TRY(run_chunk(t, c, 0, compact, n_tokens, &times));
-    KP_CUDA(cudaEventRecord(t->ev[EV_END], st));
-    KP_TRY(kp_wait_stream(t));
+    KP_TRY(run_chunk(t, c, 0, compact, n_tokens, &times));     // returns with the stream drained, EV_END recorded behind the pack
     store_times(t, times);
     cudaEventElapsedTime(&t->profile.total_ms, t->ev[EV_START], t->ev[EV_END]);
     *used = c;

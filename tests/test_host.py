@@ -532,3 +532,38 @@ def test_builder_csv_is_as_strict_as_the_reference():
                 "a,1,2,99999999999999999999\n"]:  # cost beyond i64
         with pytest.raises(BuilderError):
             _read_records(bad, "t.csv")
+
+
+def test_rust_shim_declarations_match_the_header():
+    """integration/rust/ cannot be compiled here (no Rust toolchain), so at least its extern "C" block is held
+    against include/kanpyo_b200.h: every function it declares exists there with the same number of parameters,
+    and the record structs it mirrors have the header's fields in the header's order."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "kanpyo_b200.h"), encoding="utf-8").read()
+    rs = open(os.path.join(root, "integration", "rust", "src", "ffi.rs"), encoding="utf-8").read()
+    hdr_nc = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+
+    def n_params(arglist):
+        arglist = arglist.strip()
+        return 0 if arglist in ("", "void") else arglist.count(",") + 1
+
+    c_protos = {m.group(1): n_params(m.group(2)) for m in re.finditer(r"\b(kp_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", hdr_nc)}
+    rs_nc = re.sub(r"//[^\n]*", " ", rs)
+    rs_protos = {m.group(1): n_params(m.group(2).rstrip().rstrip(","))
+                 for m in re.finditer(r"pub fn (kp_[a-z0-9_]+)\s*\(([^()]*)\)", rs_nc)}
+    assert len(rs_protos) >= 20
+    for name, n in rs_protos.items():
+        assert name in c_protos, "%s is declared in ffi.rs but not in the header" % name
+        assert c_protos[name] == n, "%s: %d parameters in ffi.rs, %d in the header" % (name, n, c_protos[name])
+
+    def c_fields(struct):
+        body = re.search(r"typedef struct %s\s*\{(.*?)\}\s*%s\s*;" % (struct, struct), hdr_nc, flags=re.S).group(1)
+        return [re.search(r"(\w+)\s*(\[[^\]]*\])?\s*$", d.strip()).group(1) for d in body.split(";") if d.strip()]
+
+    def rs_fields(struct):
+        body = re.search(r"pub struct %s\s*\{(.*?)\}" % struct, rs_nc, flags=re.S).group(1)
+        return re.findall(r"pub (\w+)\s*:", body)
+
+    for struct in ("kp_token", "kp_token8", "kp_result", "kp_result8"):
+        assert rs_fields(struct) == c_fields(struct), struct

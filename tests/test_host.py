@@ -32,6 +32,13 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, n), "libkanpyo_b200.so does not export %s" % n
         assert n in _lib.SYMBOLS, "ctypes binding misses %s" % n
     assert sorted(_lib.SYMBOLS) == names, "binding declares symbols the header does not"
+    # ... with as many parameters as the header's prototypes
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "kanpyo_b200.h"), encoding="utf-8").read(), flags=re.S)
+    for m in re.finditer(r"\b(kp_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", text):
+        args = m.group(2).strip()
+        n = 0 if args in ("", "void") else args.count(",") + 1
+        assert len(_lib.SYMBOLS[m.group(1)][1]) == n, "%s: ctypes binding has %d parameters, the header %d" % (
+            m.group(1), len(_lib.SYMBOLS[m.group(1)][1]), n)
     assert L.kp_abi_version() == 2
     assert L.kp_strerror(-2).decode().startswith("CUDA error or no usable device")
 
